@@ -1,0 +1,229 @@
+"""ctypes binding of include/coati_gpu.h (no torch types, no compute on the Python side)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+_fp = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+
+
+class CoatiGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"coati_gpu error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libcoati_gpu.so")
+
+
+def load_library() -> C.CDLL:
+    """Load libcoati_gpu.so.  There is no fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA extension is the product; there is no CPU path)")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.coati_gpu_init.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.coati_gpu_shutdown.argtypes = [vp]
+    lib.coati_gpu_shutdown.restype = None
+    lib.coati_gpu_strerror.argtypes = [C.c_int]
+    lib.coati_gpu_strerror.restype = C.c_char_p
+    lib.coati_gpu_last_cuda_error.argtypes = [vp]
+    lib.coati_gpu_last_cuda_error.restype = C.c_char_p
+    lib.coati_gpu_stream.argtypes = [vp]
+    lib.coati_gpu_stream.restype = vp
+    lib.coati_gpu_launch_count.argtypes = [vp]
+    lib.coati_gpu_launch_count.restype = C.c_uint64
+    lib.coati_gpu_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.coati_gpu_set_model.argtypes = [vp, _fp, C.c_float, C.c_float, C.c_uint32]
+    lib.coati_gpu_viterbi.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, C.c_char_p, C.c_char_p,
+                                      C.c_char_p, C.c_char_p, C.POINTER(C.c_size_t), _fp]
+    lib.coati_gpu_viterbi_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, vp, vp,
+                                            _u64p, _fp, _i32p]
+    lib.coati_gpu_batch_create.argtypes = [vp, C.c_size_t, _u64p, _u64p, C.POINTER(vp)]
+    lib.coati_gpu_batch_upload.argtypes = [vp, vp, vp, vp, vp]
+    lib.coati_gpu_batch_run.argtypes = [vp]
+    lib.coati_gpu_batch_download.argtypes = [vp, vp, vp, _u64p, _fp, _i32p]
+    lib.coati_gpu_batch_stats.argtypes = [vp, _u64p, _u64p, _u64p, _u64p]
+    lib.coati_gpu_batch_destroy.argtypes = [vp]
+    lib.coati_gpu_batch_destroy.restype = None
+    lib.coati_gpu_viterbi_directions.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, _u8p, _fp]
+    _LIB = lib
+    return lib
+
+
+def _vp(arr: np.ndarray):
+    return C.c_void_p(arr.ctypes.data)
+
+
+class PackedPairs:
+    """CSR pack of a batch (the layout of coati_gpu_viterbi_batch)."""
+
+    def __init__(self, a_list, b_list, anc_list, des_list):
+        n = len(a_list)
+        self.n = n
+        la = np.fromiter((len(x) for x in a_list), dtype=np.uint64, count=n)
+        lb = np.fromiter((len(x) for x in b_list), dtype=np.uint64, count=n)
+        self.a_off = np.zeros(n + 1, dtype=np.uint64)
+        self.b_off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(la, out=self.a_off[1:])
+        np.cumsum(lb, out=self.b_off[1:])
+        cat = lambda xs, dt: (np.concatenate([np.asarray(x, dtype=dt) for x in xs])  # noqa: E731
+                              if n and sum(len(x) for x in xs) else np.zeros(0, dtype=dt))
+        self.a_all = np.ascontiguousarray(cat(a_list, np.uint8))
+        self.b_all = np.ascontiguousarray(cat(b_list, np.uint8))
+        self.anc_all = np.frombuffer("".join(anc_list).encode("latin-1"), dtype=np.uint8).copy()
+        self.des_all = np.frombuffer("".join(des_list).encode("latin-1"), dtype=np.uint8).copy()
+        assert len(self.anc_all) == len(self.a_all) and len(self.des_all) == len(self.b_all)
+        self.out_off = self.a_off[:-1] + self.b_off[:-1] + np.arange(n, dtype=np.uint64)
+        self.out_total = int(self.a_off[-1] + self.b_off[-1]) + n
+
+    def cells(self) -> int:
+        la = np.diff(self.a_off).astype(np.float64)
+        lb = np.diff(self.b_off).astype(np.float64)
+        return int((la * lb).sum())
+
+
+class Batch:
+    def __init__(self, ctx: "Context", a_off: np.ndarray, b_off: np.ndarray):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.n = len(a_off) - 1
+        self.h = C.c_void_p()
+        self._a_off = np.ascontiguousarray(a_off, dtype=np.uint64)
+        self._b_off = np.ascontiguousarray(b_off, dtype=np.uint64)
+        ctx._check(self.lib.coati_gpu_batch_create(ctx.h, self.n, self._a_off.ctypes.data_as(_u64p),
+                                                   self._b_off.ctypes.data_as(_u64p), C.byref(self.h)))
+
+    def upload(self, a_all, b_all, anc_all, des_all):
+        self.ctx._check(self.lib.coati_gpu_batch_upload(self.h, _vp(a_all), _vp(b_all), _vp(anc_all),
+                                                        _vp(des_all)))
+
+    def run(self):
+        self.ctx._check(self.lib.coati_gpu_batch_run(self.h))
+
+    def download(self, out_a, out_b, out_len, score, status):
+        self.ctx._check(self.lib.coati_gpu_batch_download(
+            self.h, _vp(out_a), _vp(out_b), out_len.ctypes.data_as(_u64p), score.ctypes.data_as(_fp),
+            status.ctypes.data_as(_i32p)))
+
+    def stats(self):
+        v = [C.c_uint64(0) for _ in range(4)]
+        self.ctx._check(self.lib.coati_gpu_batch_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(cells=v[0].value, dir_bytes=v[1].value, launches=v[2].value, chunks=v[3].value)
+
+    def destroy(self):
+        if self.h:
+            self.lib.coati_gpu_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU context (coati_gpu_ctx).  Raises CoatiGpuError on any failure -- never falls back."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.coati_gpu_init(device, C.byref(self.h))
+        if rc != 0:
+            raise CoatiGpuError(rc, self.lib.coati_gpu_strerror(rc).decode())
+        self.k = None
+
+    def _check(self, rc: int):
+        if rc != 0:
+            extra = self.lib.coati_gpu_last_cuda_error(self.h).decode() if self.h else ""
+            raise CoatiGpuError(rc, self.lib.coati_gpu_strerror(rc).decode() + (" [" + extra + "]" if extra else ""))
+
+    def close(self):
+        if self.h:
+            self.lib.coati_gpu_shutdown(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.coati_gpu_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.coati_gpu_launch_count(self.h))
+
+    def device_info(self):
+        sm, khz = C.c_int(0), C.c_int(0)
+        fr, tot = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.coati_gpu_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(fr), C.byref(tot)))
+        return dict(sm_count=sm.value, clock_khz=khz.value, free_bytes=fr.value, total_bytes=tot.value)
+
+    def set_model(self, table, gap_open=0.001, gap_extend=1.0 - 1.0 / 6.0, gap_len=1):
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        assert t.shape == (183, 15)
+        self._check(self.lib.coati_gpu_set_model(self.h, t.ctypes.data_as(_fp), np.float32(gap_open),
+                                                 np.float32(gap_extend), int(gap_len)))
+        self.k = int(gap_len)
+
+    def viterbi(self, a, b, anc: str, des: str):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        n = len(a) + len(b) + 1
+        oa, ob = C.create_string_buffer(n), C.create_string_buffer(n)
+        ol, sc = C.c_size_t(0), C.c_float(0)
+        self._check(self.lib.coati_gpu_viterbi(self.h, a.ctypes.data_as(_u8p), len(a), b.ctypes.data_as(_u8p),
+                                               len(b), anc.encode("latin-1"), des.encode("latin-1"), oa, ob,
+                                               C.byref(ol), C.byref(sc)))
+        return oa.raw[:ol.value].decode("latin-1"), ob.raw[:ol.value].decode("latin-1"), np.float32(sc.value)
+
+    def viterbi_batch(self, pack: PackedPairs):
+        """Returns (rows_a, rows_b, scores float32[n], status int32[n]) in input order."""
+        out_a = np.zeros(pack.out_total + 1, dtype=np.uint8)
+        out_b = np.zeros(pack.out_total + 1, dtype=np.uint8)
+        out_len = np.zeros(pack.n, dtype=np.uint64)
+        score = np.zeros(pack.n, dtype=np.float32)
+        status = np.zeros(pack.n, dtype=np.int32)
+        self._check(self.lib.coati_gpu_viterbi_batch(
+            self.h, pack.n, _vp(pack.a_all), pack.a_off.ctypes.data_as(_u64p), _vp(pack.b_all),
+            pack.b_off.ctypes.data_as(_u64p), _vp(pack.anc_all), _vp(pack.des_all), _vp(out_a), _vp(out_b),
+            out_len.ctypes.data_as(_u64p), score.ctypes.data_as(_fp), status.ctypes.data_as(_i32p)))
+        rows_a, rows_b = [], []
+        for p in range(pack.n):
+            o, n = int(pack.out_off[p]), int(out_len[p])
+            rows_a.append(out_a[o:o + n].tobytes().decode("latin-1"))
+            rows_b.append(out_b[o:o + n].tobytes().decode("latin-1"))
+        return rows_a, rows_b, score, status
+
+    def batch(self, a_off, b_off) -> Batch:
+        return Batch(self, a_off, b_off)
+
+    def directions(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        d = np.zeros((len(a), len(b)), dtype=np.uint8)
+        term = np.zeros(3, dtype=np.float32)
+        self._check(self.lib.coati_gpu_viterbi_directions(self.h, a.ctypes.data_as(_u8p), len(a),
+                                                          b.ctypes.data_as(_u8p), len(b),
+                                                          d.ctypes.data_as(_u8p), term.ctypes.data_as(_fp)))
+        return d, term

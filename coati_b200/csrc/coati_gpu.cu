@@ -1,0 +1,510 @@
+// libcoati_gpu.so -- C ABI (include/coati_gpu.h) over the sm_100a marginal Gotoh kernels.
+//
+// Host side of the hot path: model upload, batch planning (length-ordered work list, direction
+// buffer chunks), kernel launches on one stream per context, result gathering.  No CPU fallback:
+// if CUDA is unavailable every entry point returns COATI_GPU_E_CUDA.
+#include "../../include/coati_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "traceback.cuh"
+#include "viterbi_generic.cuh"
+
+using namespace coati_gpu;
+
+// ---------------------------------------------------------------------------------------------
+struct coati_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    bool model_set = false;
+    GapConsts gap{};
+    float* d_table = nullptr;  // TABLE_ROWS x TABLE_LD
+    uint64_t launches = 0;
+    std::string last_error;
+    size_t dir_budget = 0;  // 0 = derive from free memory
+};
+
+#define CU_TRY(ctx, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if(e_ != cudaSuccess) {                                                             \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e_);         \
+            cudaGetLastError();                                                             \
+            return e_ == cudaErrorMemoryAllocation ? COATI_GPU_E_NOMEM : COATI_GPU_E_CUDA;  \
+        }                                                                                   \
+    } while(0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if(count == 0) return cudaSuccess;
+        return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    }
+    void release() {
+        if(p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct Chunk {
+    uint32_t first, last;  // range in sorted order
+    uint64_t dir_bytes;
+    uint32_t max_la;
+};
+
+}  // namespace
+
+struct coati_gpu_batch {
+    coati_gpu_ctx* ctx = nullptr;
+    size_t npairs = 0;
+    uint64_t a_total = 0, b_total = 0, out_total = 0;
+    std::vector<PairDesc> descs;  // sorted (largest lattice first)
+    std::vector<Chunk> chunks;
+    std::vector<int32_t> host_status;  // validation done at create time (caller order)
+    uint64_t cells = 0, dir_bytes = 0, launches = 0;
+    DevBuf<uint8_t> d_a, d_b, d_dirs;
+    DevBuf<char> d_anc, d_des, d_out_a, d_out_b;
+    DevBuf<PairDesc> d_pairs;
+    DevBuf<PairResult> d_results;
+    DevBuf<unsigned int> d_counters;
+    DevBuf<float> d_ring;
+    uint32_t ring_stride = 0, ring_ctas = 0;
+    std::vector<PairResult> h_results;
+};
+
+// ---------------------------------------------------------------------------------------------
+extern "C" const char* coati_gpu_strerror(int code) {
+    switch(code) {
+    case COATI_GPU_OK: return "success";
+    case COATI_GPU_E_CUDA: return "CUDA failure or no usable sm_100 device (there is no CPU fallback).";
+    case COATI_GPU_E_ARG: return "Invalid argument.";
+    case COATI_GPU_E_NOMEM: return "sequences to align exceed available memory.";
+    case COATI_GPU_E_SYMBOL: return "Encoded symbol outside the substitution table.";
+    case COATI_GPU_E_LENGTH:
+        return "Length of sequence must be multiple of gap unit length.";
+    case COATI_GPU_E_AMBIGUOUS: return "Ambiguous nucleotides in ancestor/reference.";
+    case COATI_GPU_E_STOP: return "Early stop codon in ancestor/reference.";
+    case COATI_GPU_E_INTERNAL: return "Traceback left the lattice.";
+    default: return "Unknown error.";
+    }
+}
+
+extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
+    if(!out) return COATI_GPU_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return COATI_GPU_E_CUDA;
+    }
+    auto* ctx = new(std::nothrow) coati_gpu_ctx;
+    if(!ctx) return COATI_GPU_E_NOMEM;
+    ctx->device = device;
+    if(cudaSetDevice(device) != cudaSuccess ||
+       cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaMalloc(reinterpret_cast<void**>(&ctx->d_table),
+                  TABLE_ROWS * TABLE_LD * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return COATI_GPU_E_CUDA;
+    }
+    if(const char* env = std::getenv("COATI_GPU_DIR_BUDGET_MB")) {
+        ctx->dir_budget = static_cast<size_t>(std::strtoull(env, nullptr, 10)) << 20;
+    }
+    *out = ctx;
+    return COATI_GPU_OK;
+}
+
+extern "C" void coati_gpu_shutdown(coati_gpu_ctx* ctx) {
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    if(ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if(ctx->d_table) cudaFree(ctx->d_table);
+    delete ctx;
+}
+
+extern "C" const char* coati_gpu_last_cuda_error(coati_gpu_ctx* ctx) {
+    return ctx ? ctx->last_error.c_str() : "";
+}
+extern "C" void* coati_gpu_stream(coati_gpu_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+extern "C" uint64_t coati_gpu_launch_count(coati_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int coati_gpu_device_info(coati_gpu_ctx* ctx, int* sm_count, int* clock_khz,
+                                     size_t* free_bytes, size_t* total_bytes) {
+    if(!ctx) return COATI_GPU_E_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if(sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if(clock_khz) {
+        int khz = 0;
+        CU_TRY(ctx, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device));
+        *clock_khz = khz;
+    }
+    size_t f = 0, t = 0;
+    CU_TRY(ctx, cudaMemGetInfo(&f, &t));
+    if(free_bytes) *free_bytes = f;
+    if(total_bytes) *total_bytes = t;
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float g, float e,
+                                   uint32_t k) {
+    if(!ctx || !table || k == 0) return COATI_GPU_E_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    // align_pair.cc:66-69 -- host libm, float, same calls as the reference
+    GapConsts c;
+    c.ng = ::log1pf(-g);
+    c.gs = ::log1pf(-e);
+    c.go = ::logf(g);
+    c.ge = ::logf(e);
+    c.gk1 = c.ge * static_cast<float>(static_cast<size_t>(k - 1));  // semiring.hpp:109-111
+    c.gk = c.ge * static_cast<float>(static_cast<size_t>(k));
+    c.k = k;
+    std::vector<float> padded(TABLE_ROWS * TABLE_LD, 0.0f);
+    for(int r = 0; r < TABLE_ROWS; ++r)
+        for(int col = 0; col < TABLE_COLS; ++col)
+            padded[r * TABLE_LD + col] = table[r * TABLE_COLS + col];
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_table, padded.data(), padded.size() * sizeof(float),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->gap = c;
+    ctx->model_set = true;
+    return COATI_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// symbol validation: a < 183, b < 15 (the reference indexes the table unchecked, matrix.hpp:73-76)
+__global__ void validate_symbols_kernel(const PairDesc* __restrict__ pairs, uint32_t npairs,
+                                        const uint8_t* __restrict__ a_all,
+                                        const uint8_t* __restrict__ b_all,
+                                        PairResult* __restrict__ results) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(warp >= npairs) return;
+    const PairDesc pd = pairs[warp];
+    bool bad = false;
+    for(uint32_t x = lane; x < pd.la; x += 32) bad |= a_all[pd.a_off + x] >= TABLE_ROWS;
+    for(uint32_t x = lane; x < pd.lb; x += 32) bad |= b_all[pd.b_off + x] >= TABLE_COLS;
+    if(__any_sync(0xffffffffu, bad) && lane == 0 && results[pd.orig].status == 0)
+        results[pd.orig].status = COATI_GPU_E_SYMBOL;
+}
+
+extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const uint64_t* a_off,
+                                      const uint64_t* b_off, coati_gpu_batch** out) {
+    if(!ctx || !out || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
+    if(!ctx->model_set || npairs > 0xfffffff0ull) return COATI_GPU_E_ARG;
+    *out = nullptr;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<coati_gpu_batch> holder(new(std::nothrow) coati_gpu_batch);
+    coati_gpu_batch* bt = holder.get();
+    if(!bt) return COATI_GPU_E_NOMEM;
+    bt->ctx = ctx;
+    bt->npairs = npairs;
+    const uint32_t k = ctx->gap.k;
+    try {
+        bt->descs.resize(npairs);
+        bt->host_status.assign(npairs, COATI_GPU_OK);
+        bt->h_results.resize(npairs);
+    } catch(const std::bad_alloc&) {
+        return COATI_GPU_E_NOMEM;
+    }
+    bt->a_total = npairs ? a_off[npairs] : 0;
+    bt->b_total = npairs ? b_off[npairs] : 0;
+    bt->out_total = bt->a_total + bt->b_total + npairs;
+    for(size_t p = 0; p < npairs; ++p) {
+        PairDesc& d = bt->descs[p];
+        const uint64_t la = a_off[p + 1] - a_off[p], lb = b_off[p + 1] - b_off[p];
+        if(la > 0x7fffffffull || lb > 0x7fffffffull) return COATI_GPU_E_ARG;
+        d.a_off = a_off[p];
+        d.b_off = b_off[p];
+        d.out_off = a_off[p] + b_off[p] + p;
+        d.dir_off = 0;
+        d.la = static_cast<uint32_t>(la);
+        d.lb = static_cast<uint32_t>(lb);
+        d.orig = static_cast<uint32_t>(p);
+        d.pad = 0;
+        // the reference checks divisibility before trimming stops (utils.cc:819-837); a lattice
+        // whose terminal cell is unreachable is undefined behaviour upstream -> reject here.
+        if(la % k != 0 || lb % k != 0) bt->host_status[p] = COATI_GPU_E_LENGTH;
+    }
+    // longest-processing-time order: biggest lattices first
+    std::stable_sort(bt->descs.begin(), bt->descs.end(), [](const PairDesc& x, const PairDesc& y) {
+        return (uint64_t)x.la * x.lb > (uint64_t)y.la * y.lb;
+    });
+    // direction-buffer chunks
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t fixed = 2 * (bt->a_total + bt->b_total) + 2 * bt->out_total +
+                           npairs * (sizeof(PairDesc) + sizeof(PairResult)) + (256ull << 20);
+    uint64_t budget = ctx->dir_budget;
+    if(budget == 0) {
+        budget = free_b > fixed ? static_cast<uint64_t>((free_b - fixed) * 0.85) : 0;
+    }
+    uint64_t need_max = 0;
+    {
+        Chunk cur{0, 0, 0, 0};
+        for(uint32_t s = 0; s < npairs; ++s) {
+            PairDesc& d = bt->descs[s];
+            const bool live = bt->host_status[d.orig] == COATI_GPU_OK;
+            const uint64_t bytes = live ? (uint64_t)d.la * d.lb : 0;
+            const uint64_t padded = (bytes + 127) & ~127ull;
+            if(padded > budget) {
+                ctx->last_error = "direction stream of one pair exceeds device memory budget";
+                return COATI_GPU_E_NOMEM;
+            }
+            if(cur.dir_bytes + padded > budget && s > cur.first) {
+                cur.last = s;
+                bt->chunks.push_back(cur);
+                cur = Chunk{s, s, 0, 0};
+            }
+            d.dir_off = cur.dir_bytes;
+            cur.dir_bytes += padded;
+            cur.max_la = std::max(cur.max_la, d.la);
+            if(live) {
+                bt->cells += bytes;
+            }
+        }
+        cur.last = static_cast<uint32_t>(npairs);
+        if(cur.last > cur.first) bt->chunks.push_back(cur);
+        for(const Chunk& c : bt->chunks) need_max = std::max(need_max, c.dir_bytes);
+    }
+    bt->dir_bytes = bt->cells;
+    // device buffers
+    uint32_t max_la = 0;
+    for(const Chunk& c : bt->chunks) max_la = std::max(max_la, c.max_la);
+    bt->ring_stride = (max_la + 1 + 31) & ~31u;
+    bt->ring_ctas = static_cast<uint32_t>(
+        std::min<size_t>(npairs ? npairs : 1, (size_t)ctx->prop.multiProcessorCount * 4));
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) {
+        if(e == cudaSuccess) e = r;
+    };
+    ok(bt->d_a.alloc(bt->a_total + 1));
+    ok(bt->d_b.alloc(bt->b_total + 1));
+    ok(bt->d_anc.alloc(bt->a_total + 1));
+    ok(bt->d_des.alloc(bt->b_total + 1));
+    ok(bt->d_out_a.alloc(bt->out_total + 1));
+    ok(bt->d_out_b.alloc(bt->out_total + 1));
+    ok(bt->d_pairs.alloc(npairs + 1));
+    ok(bt->d_results.alloc(npairs + 1));
+    ok(bt->d_counters.alloc(bt->chunks.size() + 1));
+    ok(bt->d_dirs.alloc(need_max + 128));
+    ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride));
+    if(e != cudaSuccess) {
+        ctx->last_error = std::string("batch allocation: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return COATI_GPU_E_NOMEM;
+    }
+    if(npairs) {
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_pairs.p, bt->descs.data(), npairs * sizeof(PairDesc),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = holder.release();
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_upload(coati_gpu_batch* bt, const uint8_t* a_all,
+                                      const uint8_t* b_all, const char* anc_all,
+                                      const char* des_all) {
+    if(!bt) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = bt->ctx;
+    if((bt->a_total && (!a_all || !anc_all)) || (bt->b_total && (!b_all || !des_all)))
+        return COATI_GPU_E_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if(bt->a_total) {
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_a.p, a_all, bt->a_total, cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_anc.p, anc_all, bt->a_total, cudaMemcpyHostToDevice, s));
+    }
+    if(bt->b_total) {
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_b.p, b_all, bt->b_total, cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_des.p, des_all, bt->b_total, cudaMemcpyHostToDevice, s));
+    }
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
+    if(!bt) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = bt->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = static_cast<uint32_t>(bt->npairs);
+    bt->launches = 0;
+    if(n == 0) return COATI_GPU_OK;
+    // reset results (status from host-side validation)
+    for(size_t p = 0; p < bt->npairs; ++p) {
+        PairResult r{};
+        r.status = bt->host_status[p];
+        bt->h_results[p] = r;
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(bt->d_results.p, bt->h_results.data(), n * sizeof(PairResult),
+                                cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemsetAsync(bt->d_counters.p, 0, bt->d_counters.n * sizeof(unsigned int), s));
+    {
+        const uint32_t warps_per_block = 8;
+        validate_symbols_kernel<<<(n + warps_per_block - 1) / warps_per_block,
+                                  warps_per_block * 32, 0, s>>>(bt->d_pairs.p, n, bt->d_a.p,
+                                                                 bt->d_b.p, bt->d_results.p);
+        ++bt->launches;
+    }
+    for(size_t ci = 0; ci < bt->chunks.size(); ++ci) {
+        const Chunk& c = bt->chunks[ci];
+        const uint32_t cnt = c.last - c.first;
+        const uint32_t grid = std::min(cnt, bt->ring_ctas);
+        viterbi_generic_kernel<<<grid, 128, 0, s>>>(bt->d_pairs.p, c.first, c.last,
+                                                    bt->d_counters.p + ci, bt->d_a.p, bt->d_b.p,
+                                                    ctx->d_table, ctx->gap, bt->d_ring.p,
+                                                    bt->ring_stride, bt->d_dirs.p,
+                                                    bt->d_results.p);
+        traceback_kernel<DiagLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
+            bt->d_pairs.p, c.first, c.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap.k,
+            bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+        compact_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, c.first, c.last,
+                                                          bt->d_out_a.p, bt->d_out_b.p,
+                                                          bt->d_results.p);
+        bt->launches += 3;
+    }
+    ctx->launches += bt->launches;
+    CU_TRY(ctx, cudaGetLastError());
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_download(coati_gpu_batch* bt, char* out_a, char* out_b,
+                                        uint64_t* out_len, float* score, int32_t* status) {
+    if(!bt) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = bt->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if(bt->npairs == 0) return COATI_GPU_OK;
+    if(out_a)
+        CU_TRY(ctx, cudaMemcpyAsync(out_a, bt->d_out_a.p, bt->out_total, cudaMemcpyDeviceToHost, s));
+    if(out_b)
+        CU_TRY(ctx, cudaMemcpyAsync(out_b, bt->d_out_b.p, bt->out_total, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(bt->h_results.data(), bt->d_results.p,
+                                bt->npairs * sizeof(PairResult), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    for(size_t p = 0; p < bt->npairs; ++p) {
+        const PairResult& r = bt->h_results[p];
+        if(out_len) out_len[p] = r.len;
+        if(score) score[p] = r.score;
+        if(status) status[p] = r.status;
+    }
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_stats(coati_gpu_batch* bt, uint64_t* cells, uint64_t* dir_bytes,
+                                     uint64_t* launches, uint64_t* chunks) {
+    if(!bt) return COATI_GPU_E_ARG;
+    if(cells) *cells = bt->cells;
+    if(dir_bytes) *dir_bytes = bt->dir_bytes;
+    if(launches) *launches = bt->launches;
+    if(chunks) *chunks = bt->chunks.size();
+    return COATI_GPU_OK;
+}
+
+extern "C" void coati_gpu_batch_destroy(coati_gpu_batch* bt) {
+    if(!bt) return;
+    cudaSetDevice(bt->ctx->device);
+    cudaStreamSynchronize(bt->ctx->stream);
+    delete bt;
+}
+
+extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                       const uint64_t* a_off, const uint8_t* b_all,
+                                       const uint64_t* b_off, const char* anc_all,
+                                       const char* des_all, char* out_a, char* out_b,
+                                       uint64_t* out_len, float* score, int32_t* status) {
+    coati_gpu_batch* bt = nullptr;
+    int rc = coati_gpu_batch_create(ctx, npairs, a_off, b_off, &bt);
+    if(rc != COATI_GPU_OK) return rc;
+    rc = coati_gpu_batch_upload(bt, a_all, b_all, anc_all, des_all);
+    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt);
+    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_download(bt, out_a, out_b, out_len, score, status);
+    coati_gpu_batch_destroy(bt);
+    return rc;
+}
+
+extern "C" int coati_gpu_viterbi(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
+                                 size_t Lb, const char* anc, const char* des, char* out_a,
+                                 char* out_b, size_t* out_len, float* score) {
+    if(!ctx || !out_a || !out_b) return COATI_GPU_E_ARG;
+    const uint64_t a_off[2] = {0, La}, b_off[2] = {0, Lb};
+    uint64_t len = 0;
+    float sc = 0.f;
+    int32_t st = 0;
+    int rc = coati_gpu_viterbi_batch(ctx, 1, a, a_off, b, b_off, anc, des, out_a, out_b, &len, &sc,
+                                     &st);
+    if(rc != COATI_GPU_OK) return rc;
+    if(st != COATI_GPU_OK) return st;
+    if(out_len) *out_len = len;
+    if(score) *score = sc;
+    return COATI_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void unpack_dirs_diag_kernel(const uint8_t* __restrict__ dirs, uint32_t la, uint32_t lb,
+                                        uint8_t* __restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= (uint64_t)la * lb) return;
+    const uint32_t r = idx / lb + 1, c = idx % lb + 1;
+    out[idx] = dirs[dir_index_diag(r, c, la, lb)];
+}
+
+extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a, size_t La,
+                                            const uint8_t* b, size_t Lb, uint8_t* dirs,
+                                            float terminal[3]) {
+    if(!ctx || !dirs) return COATI_GPU_E_ARG;
+    const uint64_t a_off[2] = {0, La}, b_off[2] = {0, Lb};
+    coati_gpu_batch* bt = nullptr;
+    int rc = coati_gpu_batch_create(ctx, 1, a_off, b_off, &bt);
+    if(rc != COATI_GPU_OK) return rc;
+    std::vector<char> dummy_a(La + 1, 'A'), dummy_b(Lb + 1, 'A');
+    rc = coati_gpu_batch_upload(bt, a, b, dummy_a.data(), dummy_b.data());
+    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt);
+    int32_t st = 0;
+    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_download(bt, nullptr, nullptr, nullptr, nullptr, &st);
+    if(rc == COATI_GPU_OK && st != 0) rc = st;
+    if(rc == COATI_GPU_OK && La * Lb > 0) {
+        DevBuf<uint8_t> rowmajor;
+        if(rowmajor.alloc(La * Lb) != cudaSuccess) {
+            rc = COATI_GPU_E_NOMEM;
+        } else {
+            const uint64_t n = La * Lb;
+            unpack_dirs_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+                bt->d_dirs.p, (uint32_t)La, (uint32_t)Lb, rowmajor.p);
+            ++ctx->launches;
+            if(cudaMemcpyAsync(dirs, rowmajor.p, n, cudaMemcpyDeviceToHost, ctx->stream) !=
+                   cudaSuccess ||
+               cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+                ctx->last_error = cudaGetErrorString(cudaGetLastError());
+                rc = COATI_GPU_E_CUDA;
+            }
+        }
+    }
+    if(rc == COATI_GPU_OK && terminal) {
+        for(int x = 0; x < 3; ++x) terminal[x] = bt->h_results[0].term[x];
+    }
+    coati_gpu_batch_destroy(bt);
+    return rc;
+}

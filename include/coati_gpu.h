@@ -1,0 +1,111 @@
+/*
+ * coati_gpu.h -- C ABI of the B200-native marginal Gotoh hot path (libcoati_gpu.so).
+ *
+ * The reference (CartwrightLab/coati) has no plugin/FFI seam; its only boundary for this path is
+ * the C++ free-function family in src/include/coati/align_pair.hpp:157-182, called from
+ * src/lib/align_marginal.cc:71,80 (alignpair), :586,590 (sample) and src/lib/align_msa.cc:307-308.
+ * Each entry point below names the reference call(s) it replaces.  Plain pointers and sizes only;
+ * no C++ or torch types.  All functions return COATI_GPU_OK (0) or a negative error code;
+ * coati_gpu_strerror() gives the message the C++ wrapper rethrows with.
+ *
+ * Conventions
+ *   - a   : ancestor encoded as codon61*3+phase in [0,183)   (utils.cc:496-520)
+ *   - b   : descendant encoded as IUPAC code in [0,15)        (utils.cc:522-526, utils.hpp:54-61)
+ *   - anc/des : the raw (case-preserved, end-stop-trimmed) symbols the alignment rows are made of
+ *   - table : 183 x 15 float32 row-major log-odds (mutation_coati.cc:164-202)
+ *   - scores are float32 and bit-identical to the reference's for Viterbi
+ *   - a context is bound to one GPU and is not thread-safe; use one per host thread / device
+ *   - there is NO CPU fallback: every entry point fails with COATI_GPU_E_CUDA when no device runs it
+ */
+#ifndef COATI_GPU_H
+#define COATI_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COATI_GPU_OK 0
+#define COATI_GPU_E_CUDA -1      /* CUDA runtime/driver failure or no usable device            */
+#define COATI_GPU_E_ARG -2       /* invalid argument (null pointer, k == 0, model not set ...) */
+#define COATI_GPU_E_NOMEM -3     /* device or host allocation failed (reference: std::bad_alloc) */
+#define COATI_GPU_E_SYMBOL -4    /* encoded symbol outside the table (a >= 183 or b >= 15)      */
+#define COATI_GPU_E_LENGTH -5    /* La % k != 0 or Lb % k != 0 (unreachable terminal cell)      */
+#define COATI_GPU_E_AMBIGUOUS -6 /* "Ambiguous nucleotides in ancestor/reference."              */
+#define COATI_GPU_E_STOP -7      /* "Early stop codon in ancestor/reference."                   */
+#define COATI_GPU_E_INTERNAL -8  /* traceback left the lattice (would be UB in the reference)   */
+
+typedef struct coati_gpu_ctx coati_gpu_ctx;
+typedef struct coati_gpu_batch coati_gpu_batch;
+typedef struct coati_gpu_forward_t coati_gpu_forward_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int coati_gpu_init(int device, coati_gpu_ctx** ctx);
+void coati_gpu_shutdown(coati_gpu_ctx* ctx);
+const char* coati_gpu_strerror(int code);
+/* last CUDA error string seen by this context (diagnostics) */
+const char* coati_gpu_last_cuda_error(coati_gpu_ctx* ctx);
+/* the cudaStream_t all work of this context is enqueued on (for external CUDA-event timing) */
+void* coati_gpu_stream(coati_gpu_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t coati_gpu_launch_count(coati_gpu_ctx* ctx);
+int coati_gpu_device_info(coati_gpu_ctx* ctx, int* sm_count, int* clock_khz, size_t* free_bytes,
+                          size_t* total_bytes);
+
+/* ---- model -----------------------------------------------------------------------------------
+ * Replaces what forward_impl/traceback read from `alignment_t`: aln.subst_matrix, aln.gap.open,
+ * aln.gap.extend, aln.gap.len (align_pair.cc:66-72, 253-256).  log(1-g), log(1-e), log(g), log(e),
+ * log(e)*(k-1), log(e)*k are derived on the host with libm exactly as align_pair.cc:66-69 does. */
+int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float gap_open, float gap_extend,
+                        uint32_t gap_len);
+
+/* ---- Viterbi, one pair ------------------------------------------------------------------------
+ * = viterbi_mem (align_pair.cc:195-198) + traceback_viterbi (:319-323) as marg_alignment calls
+ * them (align_marginal.cc:69-80).  out_a/out_b: caller buffers of >= La+Lb+1 bytes (NUL added). */
+int coati_gpu_viterbi(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b, size_t Lb,
+                      const char* anc, const char* des, char* out_a, char* out_b, size_t* out_len,
+                      float* score);
+
+/* ---- Viterbi, batch of independent pairs (CSR) ------------------------------------------------
+ * The same two reference calls per pair, for npairs pairs (the batch the msa driver issues per
+ * leaf, align_msa.cc:285-318, and BASELINE configs 4/5).  Pair p owns a_all[a_off[p]..a_off[p+1])
+ * and b_all[b_off[p]..b_off[p+1]); anc_all/des_all share those offsets.  Outputs for pair p start
+ * at byte a_off[p] + b_off[p] + p of out_a/out_b (capacity La+Lb+1, NUL-terminated); out_len[p],
+ * score[p], status[p] (COATI_GPU_OK or a per-pair error) are in input order.
+ * Returns COATI_GPU_OK when the batch ran, even if some pairs carry a non-zero status. */
+int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                            const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
+                            const char* anc_all, const char* des_all, char* out_a, char* out_b,
+                            uint64_t* out_len, float* score, int32_t* status);
+
+/* Staged form of the same call, so the device-resident part can be timed alone:
+ *   create  : host-side plan (length-binned LPT order, direction-buffer chunks) + device buffers
+ *   upload  : H2D of sequences        run : fill + traceback kernels only (async on the stream)
+ *   download: D2H of rows/scores      destroy
+ * `run` may be repeated; it recomputes everything from the device-resident inputs. */
+int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const uint64_t* a_off,
+                           const uint64_t* b_off, coati_gpu_batch** batch);
+int coati_gpu_batch_upload(coati_gpu_batch* batch, const uint8_t* a_all, const uint8_t* b_all,
+                           const char* anc_all, const char* des_all);
+int coati_gpu_batch_run(coati_gpu_batch* batch);
+int coati_gpu_batch_download(coati_gpu_batch* batch, char* out_a, char* out_b, uint64_t* out_len,
+                             float* score, int32_t* status);
+/* counters of the last run: lattice cells filled, direction bytes written, kernels launched */
+int coati_gpu_batch_stats(coati_gpu_batch* batch, uint64_t* cells, uint64_t* dir_bytes,
+                          uint64_t* launches, uint64_t* chunks);
+void coati_gpu_batch_destroy(coati_gpu_batch* batch);
+
+/* ---- debugging / parity aid -------------------------------------------------------------------
+ * Fill one pair and return the packed direction byte of every body cell, row-major La x Lb
+ * (bits 0-1: next state after a MATCH step lands on the cell, bits 2-3: after a DELETION step,
+ * bit 4: after an INSERTION step; 0 = M, 1 = D, 2 = I) plus the three adjusted terminal scores.
+ * This is the stream the fill kernels emit in place of the reference's three score matrices. */
+int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
+                                 size_t Lb, uint8_t* dirs, float terminal[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COATI_GPU_H */
