@@ -222,8 +222,8 @@ class Context:
         a = np.ascontiguousarray(a, dtype=np.uint8)
         b = np.ascontiguousarray(b, dtype=np.uint8)
         d = np.zeros((len(a), len(b)), dtype=np.uint8)
-        term = np.zeros(3, dtype=np.float32)
+        score = C.c_float(0)
         self._check(self.lib.coati_gpu_viterbi_directions(self.h, a.ctypes.data_as(_u8p), len(a),
                                                           b.ctypes.data_as(_u8p), len(b),
-                                                          d.ctypes.data_as(_u8p), term.ctypes.data_as(_fp)))
-        return d, term
+                                                          d.ctypes.data_as(_u8p), C.byref(score)))
+        return d, np.float32(score.value)

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "traceback.cuh"
 #include "viterbi_generic.cuh"
+#include "viterbi_pipe.cuh"
 
 using namespace coati_gpu;
 
@@ -32,6 +33,7 @@ struct coati_gpu_ctx {
     uint64_t launches = 0;
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
+    bool force_generic = false;
 };
 
 #define CU_TRY(ctx, expr)                                                                   \
@@ -70,6 +72,34 @@ struct Chunk {
     uint32_t max_la;
 };
 
+// a run of pairs inside a chunk that share one kernel configuration
+struct Run {
+    uint32_t first, last, cfg, chunk;
+};
+
+// ---- pipelined-kernel registry ------------------------------------------------------------------
+typedef void (*pipe_kernel_t)(const PairDesc*, uint32_t, uint32_t, unsigned int*, const uint8_t*,
+                              const uint8_t*, const float*, GapConsts, float4*, uint32_t, uint8_t*,
+                              PairResult*);
+struct PipeCfg {
+    uint32_t k, R;
+    pipe_kernel_t fn;
+    size_t smem;
+    int ctas_per_sm;
+};
+template <int K, int R>
+PipeCfg make_cfg() {
+    return PipeCfg{(uint32_t)K, (uint32_t)R, viterbi_pipe_kernel<K, R>,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
+}
+PipeCfg g_pipe_cfgs[] = {make_cfg<1, 4>(), make_cfg<1, 8>(), make_cfg<3, 3>(), make_cfg<3, 6>()};
+
+// issue-slot model of one pair on one warp: bands x steps x (R cells + per-step overhead)
+double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
+    const double nbands = (la + 32 * R - 1) / (32 * R);
+    return nbands * (lb + 31.0) * (R * 22.0 + 18.0);
+}
+
 }  // namespace
 
 struct coati_gpu_batch {
@@ -78,6 +108,7 @@ struct coati_gpu_batch {
     uint64_t a_total = 0, b_total = 0, out_total = 0;
     std::vector<PairDesc> descs;  // sorted (largest lattice first)
     std::vector<Chunk> chunks;
+    std::vector<Run> runs;
     std::vector<int32_t> host_status;  // validation done at create time (caller order)
     uint64_t cells = 0, dir_bytes = 0, launches = 0;
     DevBuf<uint8_t> d_a, d_b, d_dirs;
@@ -86,7 +117,8 @@ struct coati_gpu_batch {
     DevBuf<PairResult> d_results;
     DevBuf<unsigned int> d_counters;
     DevBuf<float> d_ring;
-    uint32_t ring_stride = 0, ring_ctas = 0;
+    DevBuf<float4> d_bnd;
+    uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
     std::vector<PairResult> h_results;
 };
 
@@ -129,6 +161,18 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     }
     if(const char* env = std::getenv("COATI_GPU_DIR_BUDGET_MB")) {
         ctx->dir_budget = static_cast<size_t>(std::strtoull(env, nullptr, 10)) << 20;
+    }
+    if(const char* env = std::getenv("COATI_GPU_FORCE_GENERIC")) ctx->force_generic = env[0] == '1';
+    for(PipeCfg& pc : g_pipe_cfgs) {
+        if(cudaFuncSetAttribute(pc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem) !=
+               cudaSuccess ||
+           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pc.ctas_per_sm, pc.fn, PIPE_WARPS * 32,
+                                                         pc.smem) != cudaSuccess ||
+           pc.ctas_per_sm < 1) {
+            cudaGetLastError();
+            coati_gpu_shutdown(ctx);
+            return COATI_GPU_E_CUDA;
+        }
     }
     *out = ctx;
     return COATI_GPU_OK;
@@ -242,13 +286,22 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
         d.la = static_cast<uint32_t>(la);
         d.lb = static_cast<uint32_t>(lb);
         d.orig = static_cast<uint32_t>(p);
-        d.pad = 0;
+        d.cfg = 0;
+        if(!ctx->force_generic && la > 0 && lb > 0) {
+            double best = 0;
+            for(const PipeCfg& pc : g_pipe_cfgs) {
+                if(pc.k != k) continue;
+                const double c = pipe_cost(d.la, d.lb, pc.R);
+                if(d.cfg == 0 || c < best) best = c, d.cfg = pc.R;
+            }
+        }
         // the reference checks divisibility before trimming stops (utils.cc:819-837); a lattice
         // whose terminal cell is unreachable is undefined behaviour upstream -> reject here.
         if(la % k != 0 || lb % k != 0) bt->host_status[p] = COATI_GPU_E_LENGTH;
     }
     // longest-processing-time order: biggest lattices first
     std::stable_sort(bt->descs.begin(), bt->descs.end(), [](const PairDesc& x, const PairDesc& y) {
+        if(x.cfg != y.cfg) return x.cfg > y.cfg;
         return (uint64_t)x.la * x.lb > (uint64_t)y.la * y.lb;
     });
     // direction-buffer chunks
@@ -266,7 +319,9 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
         for(uint32_t s = 0; s < npairs; ++s) {
             PairDesc& d = bt->descs[s];
             const bool live = bt->host_status[d.orig] == COATI_GPU_OK;
-            const uint64_t bytes = live ? (uint64_t)d.la * d.lb : 0;
+            const uint64_t cells = live ? (uint64_t)d.la * d.lb : 0;
+            const uint64_t bytes = !live || cells == 0 ? 0
+                                   : d.cfg ? pipe_dir_bytes(d.la, d.lb, d.cfg) : cells;
             const uint64_t padded = (bytes + 127) & ~127ull;
             if(padded > budget) {
                 ctx->last_error = "direction stream of one pair exceeds device memory budget";
@@ -280,21 +335,47 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
             d.dir_off = cur.dir_bytes;
             cur.dir_bytes += padded;
             cur.max_la = std::max(cur.max_la, d.la);
-            if(live) {
-                bt->cells += bytes;
-            }
+            bt->cells += cells;
+            bt->dir_bytes += bytes;
         }
         cur.last = static_cast<uint32_t>(npairs);
         if(cur.last > cur.first) bt->chunks.push_back(cur);
         for(const Chunk& c : bt->chunks) need_max = std::max(need_max, c.dir_bytes);
     }
-    bt->dir_bytes = bt->cells;
+    // runs of equal kernel configuration inside each chunk
+    uint32_t max_lb_pipe = 0;
+    for(size_t ci = 0; ci < bt->chunks.size(); ++ci) {
+        const Chunk& c = bt->chunks[ci];
+        uint32_t s0 = c.first;
+        for(uint32_t s = c.first; s <= c.last; ++s) {
+            if(s == c.last || bt->descs[s].cfg != bt->descs[s0].cfg) {
+                if(s > s0) bt->runs.push_back(Run{s0, s, bt->descs[s0].cfg, (uint32_t)ci});
+                s0 = s;
+            }
+            if(s < c.last && bt->descs[s].cfg) max_lb_pipe = std::max(max_lb_pipe, bt->descs[s].lb);
+        }
+    }
+    bt->bnd_stride = (max_lb_pipe + 2 + 7) & ~7u;
+    bt->bnd_ctas = 0;
+    for(const Run& r : bt->runs) {
+        if(!r.cfg) continue;
+        for(const PipeCfg& pc : g_pipe_cfgs)
+            if(pc.k == k && pc.R == r.cfg) {
+                const uint32_t want = (r.last - r.first + PIPE_WARPS - 1) / PIPE_WARPS;
+                const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc.ctas_per_sm;
+                bt->bnd_ctas = std::max(bt->bnd_ctas, std::min(want, cap));
+            }
+    }
     // device buffers
-    uint32_t max_la = 0;
-    for(const Chunk& c : bt->chunks) max_la = std::max(max_la, c.max_la);
+    uint32_t max_la = 0, n_generic = 0;
+    for(const Run& r : bt->runs)
+        if(r.cfg == 0) {
+            n_generic += r.last - r.first;
+            for(uint32_t x = r.first; x < r.last; ++x) max_la = std::max(max_la, bt->descs[x].la);
+        }
     bt->ring_stride = (max_la + 1 + 31) & ~31u;
     bt->ring_ctas = static_cast<uint32_t>(
-        std::min<size_t>(npairs ? npairs : 1, (size_t)ctx->prop.multiProcessorCount * 4));
+        std::min<size_t>(n_generic, (size_t)ctx->prop.multiProcessorCount * 4));
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) {
         if(e == cudaSuccess) e = r;
@@ -307,7 +388,8 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     ok(bt->d_out_b.alloc(bt->out_total + 1));
     ok(bt->d_pairs.alloc(npairs + 1));
     ok(bt->d_results.alloc(npairs + 1));
-    ok(bt->d_counters.alloc(bt->chunks.size() + 1));
+    ok(bt->d_counters.alloc(bt->runs.size() + 1));
+    ok(bt->d_bnd.alloc((size_t)bt->bnd_ctas * PIPE_WARPS * 2 * bt->bnd_stride));
     ok(bt->d_dirs.alloc(need_max + 128));
     ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride));
     if(e != cudaSuccess) {
@@ -368,19 +450,36 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                                  bt->d_b.p, bt->d_results.p);
         ++bt->launches;
     }
-    for(size_t ci = 0; ci < bt->chunks.size(); ++ci) {
-        const Chunk& c = bt->chunks[ci];
-        const uint32_t cnt = c.last - c.first;
-        const uint32_t grid = std::min(cnt, bt->ring_ctas);
-        viterbi_generic_kernel<<<grid, 128, 0, s>>>(bt->d_pairs.p, c.first, c.last,
-                                                    bt->d_counters.p + ci, bt->d_a.p, bt->d_b.p,
-                                                    ctx->d_table, ctx->gap, bt->d_ring.p,
-                                                    bt->ring_stride, bt->d_dirs.p,
-                                                    bt->d_results.p);
-        traceback_kernel<DiagLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
-            bt->d_pairs.p, c.first, c.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap.k,
-            bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
-        compact_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, c.first, c.last,
+    for(size_t ri = 0; ri < bt->runs.size(); ++ri) {
+        const Run& r = bt->runs[ri];
+        const uint32_t cnt = r.last - r.first;
+        if(r.cfg == 0) {
+            const uint32_t grid = std::min(cnt, bt->ring_ctas);
+            viterbi_generic_kernel<<<grid, 128, 0, s>>>(bt->d_pairs.p, r.first, r.last,
+                                                        bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                                                        ctx->d_table, ctx->gap, bt->d_ring.p,
+                                                        bt->ring_stride, bt->d_dirs.p,
+                                                        bt->d_results.p);
+            traceback_kernel<DiagLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
+                bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
+                bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+        } else {
+            const PipeCfg* pc = nullptr;
+            for(const PipeCfg& x : g_pipe_cfgs)
+                if(x.k == ctx->gap.k && x.R == r.cfg) pc = &x;
+            if(!pc) return COATI_GPU_E_ARG;
+            const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
+            const uint32_t grid = std::min(
+                want, std::min(bt->bnd_ctas,
+                               (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm));
+            pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
+                bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p, bt->d_results.p);
+            traceback_kernel<PipeLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
+                bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
+                bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+        }
+        compact_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last,
                                                           bt->d_out_a.p, bt->d_out_b.p,
                                                           bt->d_results.p);
         bt->launches += 3;
@@ -463,17 +562,22 @@ extern "C" int coati_gpu_viterbi(coati_gpu_ctx* ctx, const uint8_t* a, size_t La
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void unpack_dirs_diag_kernel(const uint8_t* __restrict__ dirs, uint32_t la, uint32_t lb,
-                                        uint8_t* __restrict__ out) {
+// canonical decision byte per body cell, row-major, from either stream layout
+template <class Layout>
+__global__ void unpack_dirs_kernel(const uint8_t* __restrict__ dirs, PairDesc pd,
+                                   uint8_t* __restrict__ out) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(idx >= (uint64_t)la * lb) return;
-    const uint32_t r = idx / lb + 1, c = idx % lb + 1;
-    out[idx] = dirs[dir_index_diag(r, c, la, lb)];
+    if(idx >= (uint64_t)pd.la * pd.lb) return;
+    const uint32_t r = idx / pd.lb + 1, c = idx % pd.lb + 1;
+    const uint8_t* d = dirs + pd.dir_off;
+    const int x = Layout::next(d, pd, ST_M, r, c), y = Layout::next(d, pd, ST_D, r, c),
+              z = Layout::next(d, pd, ST_I, r, c);
+    out[idx] = (uint8_t)(x | (y << 2) | ((z == ST_I ? 1 : 0) << 4));
 }
 
 extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a, size_t La,
                                             const uint8_t* b, size_t Lb, uint8_t* dirs,
-                                            float terminal[3]) {
+                                            float* score) {
     if(!ctx || !dirs) return COATI_GPU_E_ARG;
     const uint64_t a_off[2] = {0, La}, b_off[2] = {0, Lb};
     coati_gpu_batch* bt = nullptr;
@@ -483,7 +587,8 @@ extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a
     rc = coati_gpu_batch_upload(bt, a, b, dummy_a.data(), dummy_b.data());
     if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt);
     int32_t st = 0;
-    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_download(bt, nullptr, nullptr, nullptr, nullptr, &st);
+    float sc = 0.f;
+    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_download(bt, nullptr, nullptr, nullptr, &sc, &st);
     if(rc == COATI_GPU_OK && st != 0) rc = st;
     if(rc == COATI_GPU_OK && La * Lb > 0) {
         DevBuf<uint8_t> rowmajor;
@@ -491,8 +596,12 @@ extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a
             rc = COATI_GPU_E_NOMEM;
         } else {
             const uint64_t n = La * Lb;
-            unpack_dirs_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-                bt->d_dirs.p, (uint32_t)La, (uint32_t)Lb, rowmajor.p);
+            const PairDesc pd = bt->descs[0];
+            const unsigned grid = (unsigned)((n + 255) / 256);
+            if(pd.cfg)
+                unpack_dirs_kernel<PipeLayout><<<grid, 256, 0, ctx->stream>>>(bt->d_dirs.p, pd, rowmajor.p);
+            else
+                unpack_dirs_kernel<DiagLayout><<<grid, 256, 0, ctx->stream>>>(bt->d_dirs.p, pd, rowmajor.p);
             ++ctx->launches;
             if(cudaMemcpyAsync(dirs, rowmajor.p, n, cudaMemcpyDeviceToHost, ctx->stream) !=
                    cudaSuccess ||
@@ -502,9 +611,7 @@ extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a
             }
         }
     }
-    if(rc == COATI_GPU_OK && terminal) {
-        for(int x = 0; x < 3; ++x) terminal[x] = bt->h_results[0].term[x];
-    }
+    if(rc == COATI_GPU_OK && score) *score = sc;
     coati_gpu_batch_destroy(bt);
     return rc;
 }

@@ -40,7 +40,7 @@ struct PairDesc {
     uint64_t out_off;  // into out_a / out_b (capacity la + lb + 1)
     uint32_t la, lb;
     uint32_t orig;     // index in caller order
-    uint32_t pad;
+    uint32_t cfg;      // 0: generic-k kernel (DiagLayout); else rows per lane R of the pipelined kernel
 };
 
 // Per-pair results (device side, caller order).

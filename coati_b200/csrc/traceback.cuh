@@ -10,10 +10,43 @@
 
 namespace coati_gpu {
 
+// Generic-k kernels: one decision byte per body cell, anti-diagonal-major (common.cuh).
 struct DiagLayout {
-    __device__ __forceinline__ static uint64_t index(uint32_t r, uint32_t c, uint32_t la,
-                                                     uint32_t lb) {
-        return dir_index_diag(r, c, la, lb);
+    __device__ __forceinline__ static int initial(const uint8_t*, const PairDesc&, PairResult& res) {
+        const float tM = res.term[0], tD = res.term[1], tI = res.term[2];
+        res.score = fmaxf(fmaxf(tM, tD), tI);  // align_pair.cc:265
+        return max_mdi(tM, tD, tI);            // :266
+    }
+    __device__ __forceinline__ static int next(const uint8_t* dir, const PairDesc& pd, int st,
+                                               uint32_t r, uint32_t c) {
+        const uint32_t byte = dir[dir_index_diag(r, c, pd.la, pd.lb)];
+        return st == ST_M ? (byte & 3) : st == ST_D ? ((byte >> 2) & 3) : ((byte >> 4) & 1) * 2;
+    }
+};
+
+// Pipelined kernels: five bit-planes per row (viterbi_pipe.cuh).  pd.cfg = R.
+struct PipeLayout {
+    __device__ __forceinline__ static uint32_t plane_bit(const uint32_t* w, const PairDesc& pd,
+                                                         uint32_t r, uint32_t c, uint32_t plane) {
+        const uint32_t R = pd.cfg, H = 32 * R, wpl = (5 * R + 3) & ~3u;
+        const uint32_t band = (r - 1) / H, rr = (r - 1) % H, lane = rr / R, q = rr % R;
+        const uint32_t t = (c - 1) + lane, nblocks = (pd.lb + 62) / 32;
+        const uint64_t idx = ((uint64_t)(band * nblocks + (t >> 5)) * 32 + lane) * wpl + q * 5 + plane;
+        return (w[idx] >> (31 - (t & 31))) & 1u;
+    }
+    __device__ __forceinline__ static int next(const uint8_t* dir, const PairDesc& pd, int st,
+                                               uint32_t r, uint32_t c) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(dir);
+        if(st == ST_I) return plane_bit(w, pd, r, c, 4) ? ST_M : ST_I;
+        const uint32_t base = st == ST_M ? 0 : 2;
+        if(plane_bit(w, pd, r, c, base)) return ST_M;
+        return plane_bit(w, pd, r, c, base + 1) ? ST_D : ST_I;
+    }
+    // score = X(La, Lb) was written by the fill; max_mdi of the adjusted terminal scores is the
+    // MATCH-lands decision of the terminal cell (align_pair.cc:130-138, 265-266).
+    __device__ __forceinline__ static int initial(const uint8_t* dir, const PairDesc& pd,
+                                                  PairResult&) {
+        return next(dir, pd, ST_M, pd.la, pd.lb);
     }
 };
 
@@ -22,7 +55,7 @@ struct DiagLayout {
 template <class Layout>
 __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                                  const uint8_t* __restrict__ dirs, const char* __restrict__ anc_all,
-                                 const char* __restrict__ des_all, uint32_t k,
+                                 const char* __restrict__ des_all, GapConsts gap,
                                  char* __restrict__ out_a, char* __restrict__ out_b,
                                  PairResult* __restrict__ results) {
     const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,17 +63,31 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
     const PairDesc pd = pairs[p];
     PairResult& res = results[pd.orig];
     if(res.status != 0) return;
-    const uint32_t la = pd.la, lb = pd.lb;
+    const uint32_t la = pd.la, lb = pd.lb, k = gap.k;
     const char* anc = anc_all + pd.a_off;
     const char* des = des_all + pd.b_off;
     const uint8_t* dir = dirs + pd.dir_off;
     char* oa = out_a + pd.out_off;
     char* ob = out_b + pd.out_off;
 
-    const float tM = res.term[0], tD = res.term[1], tI = res.term[2];
-    res.score = fmaxf(fmaxf(tM, tD), tI);  // align_pair.cc:265
-    int st = max_mdi(tM, tD, tI);          // :266
     uint32_t r = la, c = lb, pos = la + lb;
+    int st;
+    if(la == 0 || lb == 0) {
+        // no body cell: the path is the margin itself (align_pair.cc:82-90, 130-138)
+        const GapConsts g = gap;
+        if(la == 0 && lb == 0) {
+            res.score = (0.0f + g.ng) + g.ng;
+            st = ST_M;
+        } else if(la == 0) {
+            res.score = ((g.go + g.ge * (float)(lb + k - 2)) + g.gs) + g.ng;
+            st = ST_I;
+        } else {
+            res.score = ((g.ng + g.go) + g.ge * (float)(la + k - 2)) + g.gs;
+            st = ST_D;
+        }
+    } else {
+        st = Layout::initial(dir, pd, res);
+    }
     int err = 0;
     while(r > 0 || c > 0) {  // :268  (j > k-1 || i > k-1)
         if(st == ST_M) {
@@ -70,10 +117,7 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
         int nst;
         if(r == 0) nst = ST_I;        // only ins(start, j) is finite on the top margin (:88-90)
         else if(c == 0) nst = ST_D;   // only del(i, start) is finite on the left margin (:84-87)
-        else {
-            const uint32_t byte = dir[Layout::index(r, c, la, lb)];
-            nst = st == ST_M ? (byte & 3) : st == ST_D ? ((byte >> 2) & 3) : ((byte >> 4) & 1) * 2;
-        }
+        else nst = Layout::next(dir, pd, st, r, c);
         st = nst;
     }
     if(err) {

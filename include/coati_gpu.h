@@ -98,12 +98,13 @@ int coati_gpu_batch_stats(coati_gpu_batch* batch, uint64_t* cells, uint64_t* dir
 void coati_gpu_batch_destroy(coati_gpu_batch* batch);
 
 /* ---- debugging / parity aid -------------------------------------------------------------------
- * Fill one pair and return the packed direction byte of every body cell, row-major La x Lb
+ * Fill one pair and return the decision byte of every body cell, row-major La x Lb
  * (bits 0-1: next state after a MATCH step lands on the cell, bits 2-3: after a DELETION step,
- * bit 4: after an INSERTION step; 0 = M, 1 = D, 2 = I) plus the three adjusted terminal scores.
- * This is the stream the fill kernels emit in place of the reference's three score matrices. */
+ * bit 4: after an INSERTION step; 0 = M, 1 = D, 2 = I), decoded from whichever packed stream the
+ * fill kernel for this pair emits in place of the reference's three score matrices, plus the
+ * Viterbi score.  For cell-level parity tests against traceback's expressions (align_pair.cc:275-296). */
 int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
-                                 size_t Lb, uint8_t* dirs, float terminal[3]);
+                                 size_t Lb, uint8_t* dirs, float* score);
 
 #ifdef __cplusplus
 }
