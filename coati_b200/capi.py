@@ -59,6 +59,16 @@ def load_library() -> C.CDLL:
     lib.coati_gpu_batch_run.argtypes = [vp]
     lib.coati_gpu_batch_download.argtypes = [vp, vp, vp, _u64p, _fp, _i32p]
     lib.coati_gpu_batch_stats.argtypes = [vp, _u64p, _u64p, _u64p, _u64p]
+    lib.coati_gpu_batch_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double), _u64p]
+    lib.coati_gpu_batch_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), _u64p,
+                                                   C.POINTER(vp), _u64p]
+    lib.coati_synth_offsets.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
+                                        C.c_double, C.c_int, _u64p, _u64p]
+    lib.coati_synth_offsets.restype = None
+    lib.coati_synth_fill.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
+                                     C.c_double, C.c_int, _u64p, _u64p, vp, vp, vp, vp]
+    lib.coati_synth_fill.restype = None
     lib.coati_gpu_batch_destroy.argtypes = [vp]
     lib.coati_gpu_batch_destroy.restype = None
     lib.coati_gpu_viterbi_directions.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, _u8p, _fp]
@@ -125,6 +135,21 @@ class Batch:
         v = [C.c_uint64(0) for _ in range(4)]
         self.ctx._check(self.lib.coati_gpu_batch_stats(self.h, *[C.byref(x) for x in v]))
         return dict(cells=v[0].value, dir_bytes=v[1].value, launches=v[2].value, chunks=v[3].value)
+
+    def timing(self):
+        f, t, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        n = C.c_uint64(0)
+        self.ctx._check(self.lib.coati_gpu_batch_timing(self.h, C.byref(f), C.byref(t), C.byref(c),
+                                                        C.byref(n)))
+        return dict(fill_ms=f.value, traceback_ms=t.value, compact_ms=c.value, fill_launches=n.value)
+
+    def device_buffers(self):
+        oa, ob, rs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nb, rb = C.c_uint64(0), C.c_uint64(0)
+        self.ctx._check(self.lib.coati_gpu_batch_device_buffers(self.h, C.byref(oa), C.byref(ob),
+                                                                C.byref(nb), C.byref(rs), C.byref(rb)))
+        return dict(out_a=oa.value, out_b=ob.value, out_bytes=nb.value, results=rs.value,
+                    result_bytes=rb.value)
 
     def destroy(self):
         if self.h:
@@ -227,3 +252,23 @@ class Context:
                                                           b.ctypes.data_as(_u8p), len(b),
                                                           d.ctypes.data_as(_u8p), C.byref(score)))
         return d, np.float32(score.value)
+
+
+def synth_pairs(n: int, workload: int = 5, seed: int = 42, first: int = 0, sub: float = 0.05,
+                indel: float = 0.005, threads: int = 0, alloc=None):
+    """Seeded synthetic pairs.  Returns dict(a_off, b_off, a_all, b_all, anc_all,
+    des_all); `alloc(nbytes)` may supply pinned uint8 buffers."""
+    lib = load_library()
+    threads = threads or (os.cpu_count() or 1)
+    a_off = np.zeros(n + 1, dtype=np.uint64)
+    b_off = np.zeros(n + 1, dtype=np.uint64)
+    lib.coati_synth_offsets(seed, first, n, workload, sub, indel, threads, a_off.ctypes.data_as(_u64p),
+                            b_off.ctypes.data_as(_u64p))
+    alloc = alloc or (lambda nbytes: np.zeros(nbytes, dtype=np.uint8))
+    ta, tb = int(a_off[-1]), int(b_off[-1])
+    out = dict(a_off=a_off, b_off=b_off, a_all=alloc(ta + 1), b_all=alloc(tb + 1), anc_all=alloc(ta + 1),
+               des_all=alloc(tb + 1))
+    lib.coati_synth_fill(seed, first, n, workload, sub, indel, threads, a_off.ctypes.data_as(_u64p),
+                         b_off.ctypes.data_as(_u64p), _vp(out["anc_all"]), _vp(out["des_all"]),
+                         _vp(out["a_all"]), _vp(out["b_all"]))
+    return out

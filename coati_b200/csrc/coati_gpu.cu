@@ -23,6 +23,58 @@
 using namespace coati_gpu;
 
 // ---------------------------------------------------------------------------------------------
+// Grow-only device memory pool: batches borrow blocks and give them back, so repeated calls of the
+// public batch entry point do not pay cudaMalloc/cudaFree (which synchronise the device).
+struct DevPool {
+    struct Block {
+        void* p;
+        size_t bytes;
+        bool used;
+    };
+    std::vector<Block> blocks;
+    void* take(size_t bytes, cudaError_t* err) {
+        *err = cudaSuccess;
+        if(bytes == 0) return nullptr;
+        Block* best = nullptr;
+        for(Block& b : blocks)
+            if(!b.used && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+        if(best && best->bytes <= 2 * bytes + (1u << 20)) {
+            best->used = true;
+            return best->p;
+        }
+        void* p = nullptr;
+        *err = cudaMalloc(&p, bytes);
+        if(*err != cudaSuccess) {  // release idle blocks and retry once
+            cudaGetLastError();
+            trim();
+            *err = cudaMalloc(&p, bytes);
+            if(*err != cudaSuccess) return nullptr;
+        }
+        blocks.push_back(Block{p, bytes, true});
+        return p;
+    }
+    void give(void* p) {
+        for(Block& b : blocks)
+            if(b.p == p) b.used = false;
+    }
+    void trim() {
+        for(size_t i = 0; i < blocks.size();) {
+            if(!blocks[i].used) {
+                cudaFree(blocks[i].p);
+                blocks.erase(blocks.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+    }
+    size_t idle_bytes() const {
+        size_t n = 0;
+        for(const Block& b : blocks)
+            if(!b.used) n += b.bytes;
+        return n;
+    }
+};
+
 struct coati_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -34,6 +86,7 @@ struct coati_gpu_ctx {
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
     bool force_generic = false;
+    DevPool pool;
 };
 
 #define CU_TRY(ctx, expr)                                                                   \
@@ -52,14 +105,24 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaError_t alloc(size_t count) {
+    DevPool* pool = nullptr;
+    cudaError_t alloc(size_t count, DevPool* from = nullptr) {
         release();
         n = count;
+        pool = from;
         if(count == 0) return cudaSuccess;
+        if(pool) {
+            cudaError_t e;
+            p = static_cast<T*>(pool->take(count * sizeof(T), &e));
+            return e;
+        }
         return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
     }
     void release() {
-        if(p) cudaFree(p);
+        if(p) {
+            if(pool) pool->give(p);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -120,6 +183,10 @@ struct coati_gpu_batch {
     DevBuf<float4> d_bnd;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
     std::vector<PairResult> h_results;
+    std::vector<cudaEvent_t> events;  // 4 per run: fill start, fill end, traceback end, compact end
+    ~coati_gpu_batch() {
+        for(cudaEvent_t e : events) cudaEventDestroy(e);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -186,6 +253,7 @@ extern "C" void coati_gpu_shutdown(coati_gpu_ctx* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     if(ctx->d_table) cudaFree(ctx->d_table);
+    ctx->pool.trim();
     delete ctx;
 }
 
@@ -307,6 +375,7 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     // direction-buffer chunks
     size_t free_b = 0, total_b = 0;
     CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    free_b += ctx->pool.idle_bytes();
     const uint64_t fixed = 2 * (bt->a_total + bt->b_total) + 2 * bt->out_total +
                            npairs * (sizeof(PairDesc) + sizeof(PairResult)) + (256ull << 20);
     uint64_t budget = ctx->dir_budget;
@@ -380,18 +449,18 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     auto ok = [&](cudaError_t r) {
         if(e == cudaSuccess) e = r;
     };
-    ok(bt->d_a.alloc(bt->a_total + 1));
-    ok(bt->d_b.alloc(bt->b_total + 1));
-    ok(bt->d_anc.alloc(bt->a_total + 1));
-    ok(bt->d_des.alloc(bt->b_total + 1));
-    ok(bt->d_out_a.alloc(bt->out_total + 1));
-    ok(bt->d_out_b.alloc(bt->out_total + 1));
-    ok(bt->d_pairs.alloc(npairs + 1));
-    ok(bt->d_results.alloc(npairs + 1));
-    ok(bt->d_counters.alloc(bt->runs.size() + 1));
-    ok(bt->d_bnd.alloc((size_t)bt->bnd_ctas * PIPE_WARPS * 2 * bt->bnd_stride));
-    ok(bt->d_dirs.alloc(need_max + 128));
-    ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride));
+    ok(bt->d_a.alloc(bt->a_total + 1, &ctx->pool));
+    ok(bt->d_b.alloc(bt->b_total + 1, &ctx->pool));
+    ok(bt->d_anc.alloc(bt->a_total + 1, &ctx->pool));
+    ok(bt->d_des.alloc(bt->b_total + 1, &ctx->pool));
+    ok(bt->d_out_a.alloc(bt->out_total + 1, &ctx->pool));
+    ok(bt->d_out_b.alloc(bt->out_total + 1, &ctx->pool));
+    ok(bt->d_pairs.alloc(npairs + 1, &ctx->pool));
+    ok(bt->d_results.alloc(npairs + 1, &ctx->pool));
+    ok(bt->d_counters.alloc(bt->runs.size() + 1, &ctx->pool));
+    ok(bt->d_bnd.alloc((size_t)bt->bnd_ctas * PIPE_WARPS * 2 * bt->bnd_stride, &ctx->pool));
+    ok(bt->d_dirs.alloc(need_max + 128, &ctx->pool));
+    ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride, &ctx->pool));
     if(e != cudaSuccess) {
         ctx->last_error = std::string("batch allocation: ") + cudaGetErrorString(e);
         cudaGetLastError();
@@ -450,9 +519,16 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                                  bt->d_b.p, bt->d_results.p);
         ++bt->launches;
     }
+    if(bt->events.size() != 4 * bt->runs.size()) {
+        for(cudaEvent_t e : bt->events) cudaEventDestroy(e);
+        bt->events.assign(4 * bt->runs.size(), nullptr);
+        for(cudaEvent_t& e : bt->events) CU_TRY(ctx, cudaEventCreate(&e));
+    }
     for(size_t ri = 0; ri < bt->runs.size(); ++ri) {
         const Run& r = bt->runs[ri];
         const uint32_t cnt = r.last - r.first;
+        cudaEvent_t* ev = &bt->events[4 * ri];
+        cudaEventRecord(ev[0], s);
         if(r.cfg == 0) {
             const uint32_t grid = std::min(cnt, bt->ring_ctas);
             viterbi_generic_kernel<<<grid, 128, 0, s>>>(bt->d_pairs.p, r.first, r.last,
@@ -460,6 +536,7 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                         ctx->d_table, ctx->gap, bt->d_ring.p,
                                                         bt->ring_stride, bt->d_dirs.p,
                                                         bt->d_results.p);
+            cudaEventRecord(ev[1], s);
             traceback_kernel<DiagLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
                 bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
                 bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
@@ -475,13 +552,16 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
             pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
                 bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
                 ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p, bt->d_results.p);
+            cudaEventRecord(ev[1], s);
             traceback_kernel<PipeLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
                 bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
                 bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
         }
+        cudaEventRecord(ev[2], s);
         compact_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last,
                                                           bt->d_out_a.p, bt->d_out_b.p,
                                                           bt->d_results.p);
+        cudaEventRecord(ev[3], s);
         bt->launches += 3;
     }
     ctx->launches += bt->launches;
@@ -519,6 +599,41 @@ extern "C" int coati_gpu_batch_stats(coati_gpu_batch* bt, uint64_t* cells, uint6
     if(dir_bytes) *dir_bytes = bt->dir_bytes;
     if(launches) *launches = bt->launches;
     if(chunks) *chunks = bt->chunks.size();
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_timing(coati_gpu_batch* bt, double* fill_ms, double* traceback_ms,
+                                      double* compact_ms, uint64_t* fill_launches) {
+    if(!bt) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = bt->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double f = 0, t = 0, c = 0;
+    for(size_t ri = 0; 4 * ri + 3 < bt->events.size(); ++ri) {
+        float ms = 0;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[4 * ri], bt->events[4 * ri + 1]));
+        f += ms;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[4 * ri + 1], bt->events[4 * ri + 2]));
+        t += ms;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[4 * ri + 2], bt->events[4 * ri + 3]));
+        c += ms;
+    }
+    if(fill_ms) *fill_ms = f;
+    if(traceback_ms) *traceback_ms = t;
+    if(compact_ms) *compact_ms = c;
+    if(fill_launches) *fill_launches = bt->events.size() / 4;
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_device_buffers(coati_gpu_batch* bt, void** out_a, void** out_b,
+                                              uint64_t* out_bytes, void** results,
+                                              uint64_t* result_bytes) {
+    if(!bt) return COATI_GPU_E_ARG;
+    if(out_a) *out_a = bt->d_out_a.p;
+    if(out_b) *out_b = bt->d_out_b.p;
+    if(out_bytes) *out_bytes = bt->out_total;
+    if(results) *results = bt->d_results.p;
+    if(result_bytes) *result_bytes = bt->npairs * sizeof(PairResult);
     return COATI_GPU_OK;
 }
 

@@ -95,7 +95,25 @@ int coati_gpu_batch_download(coati_gpu_batch* batch, char* out_a, char* out_b, u
 /* counters of the last run: lattice cells filled, direction bytes written, kernels launched */
 int coati_gpu_batch_stats(coati_gpu_batch* batch, uint64_t* cells, uint64_t* dir_bytes,
                           uint64_t* launches, uint64_t* chunks);
+/* device time of the last run split by kernel family, from CUDA events recorded on the context's
+ * stream around each launch (synchronises the stream); fill_launches = fill kernels launched */
+int coati_gpu_batch_timing(coati_gpu_batch* batch, double* fill_ms, double* traceback_ms,
+                           double* compact_ms, uint64_t* fill_launches);
+/* device-resident outputs of the last run (for a NCCL gather of per-rank results): the two row
+ * arenas (out_bytes each, same layout as coati_gpu_viterbi_batch's out_a/out_b) and the per-pair
+ * result records {float term[3]; float score; u32 len; u32 start; i32 status; u32 pad}. */
+int coati_gpu_batch_device_buffers(coati_gpu_batch* batch, void** out_a, void** out_b,
+                                   uint64_t* out_bytes, void** results, uint64_t* result_bytes);
 void coati_gpu_batch_destroy(coati_gpu_batch* batch);
+
+/* ---- host utilities (no GPU involved) ---------------------------------------------------------
+ * Seeded synthetic workloads of SURVEY.md 8(d): workload 5 = length-binned C5 pairs, 4 = C4
+ * (300-3000 nt).  Pair p depends only on (seed, first + p).  offsets: n + 1 entries each. */
+void coati_synth_offsets(uint64_t seed, uint64_t first, uint64_t n, int workload, double sub,
+                         double indel, int threads, uint64_t* a_off, uint64_t* b_off);
+void coati_synth_fill(uint64_t seed, uint64_t first, uint64_t n, int workload, double sub,
+                      double indel, int threads, const uint64_t* a_off, const uint64_t* b_off,
+                      char* anc_all, char* des_all, uint8_t* a_all, uint8_t* b_all);
 
 /* ---- debugging / parity aid -------------------------------------------------------------------
  * Fill one pair and return the decision byte of every body cell, row-major La x Lb
