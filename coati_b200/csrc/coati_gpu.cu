@@ -19,6 +19,7 @@
 #include "traceback.cuh"
 #include "viterbi_generic.cuh"
 #include "viterbi_pipe.cuh"
+#include "viterbi_pipe1.cuh"
 
 using namespace coati_gpu;
 
@@ -155,7 +156,13 @@ PipeCfg make_cfg() {
     return PipeCfg{(uint32_t)K, (uint32_t)R, viterbi_pipe_kernel<K, R>,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
 }
-PipeCfg g_pipe_cfgs[] = {make_cfg<1, 4>(), make_cfg<1, 8>(), make_cfg<3, 3>(), make_cfg<3, 6>()};
+template <int R>
+PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation (viterbi_pipe1.cuh)
+    PipeCfg c = make_cfg<1, R>();
+    c.fn = viterbi_pipe1_kernel<R>;
+    return c;
+}
+PipeCfg g_pipe_cfgs[] = {make_cfg1<4>(), make_cfg1<8>(), make_cfg<3, 3>(), make_cfg<3, 6>()};
 
 // issue-slot model of one pair on one warp: bands x steps x (R cells + per-step overhead)
 double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
@@ -230,6 +237,12 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
         ctx->dir_budget = static_cast<size_t>(std::strtoull(env, nullptr, 10)) << 20;
     }
     if(const char* env = std::getenv("COATI_GPU_FORCE_GENERIC")) ctx->force_generic = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_PIPE_SCALAR")) {  // A/B: scalar template for K = 1
+        if(env[0] == '1') {
+            g_pipe_cfgs[0].fn = viterbi_pipe_kernel<1, 4>;
+            g_pipe_cfgs[1].fn = viterbi_pipe_kernel<1, 8>;
+        }
+    }
     for(PipeCfg& pc : g_pipe_cfgs) {
         if(cudaFuncSetAttribute(pc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem) !=
                cudaSuccess ||

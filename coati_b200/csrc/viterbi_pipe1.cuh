@@ -1,0 +1,225 @@
+// K = 1 specialisation of the register-pipelined Viterbi fill (see viterbi_pipe.cuh for the scheme
+// and the exactness argument).  Same lattice decomposition, same decision-plane stream (PipeLayout),
+// tuned for issue slots on sm_100a:
+//   * the match/insert halves of two adjacent rows are evaluated with packed add.rn.f32x2 (FADD2):
+//     nine packed adds replace eighteen scalar ones per row pair; each lane of a packed add is an
+//     IEEE round-to-nearest FADD, so results are bit-identical to the scalar form;
+//   * decisions are FSETP + predicated OR into the plane accumulators (no select/mask pair);
+//   * the symbol, the row above the band and the row below it move on uniform addresses
+//     (lane 31 carries lane 0's inputs in its outgoing shuffle registers), so the per-step
+//     overhead is three shuffles, two broadcast loads and one predicated store.
+#pragma once
+
+#include "common.cuh"
+#include "viterbi_pipe.cuh"
+
+namespace coati_gpu {
+
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 mk2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f2 a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(f2 a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return hi;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {  // two independent round-to-nearest FADDs
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
+// acc |= bm when a == b / a > b, as FSETP + predicated LOP3 (the compiler's own lowering of
+// `if(a == b) acc |= bm` is FSETP + SEL + LOP3)
+// The OR is issued as a predicated IMAD (acc += bm * one; the bit is never set twice), because the
+// ALU pipe (FSETP, FMNMX, LOP3: half rate) is the binding pipe of this kernel and the FMA pipe is not.
+__device__ __forceinline__ void or_if_eq(uint32_t& acc, float a, float b, uint32_t bm, uint32_t one) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "f"(a), "f"(b), "r"(bm), "r"(one));
+}
+__device__ __forceinline__ void or_if_gt(uint32_t& acc, float a, float b, uint32_t bm, uint32_t one) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "f"(a), "f"(b), "r"(bm), "r"(one));
+}
+
+// one row of the column: scalar D-part, maxima, decisions (align_pair.cc:97-124, 275-296)
+#define COATI_ROW(q, xmq, ymq, zmq, xiq, yiq, ziq)                                           \
+    {                                                                                        \
+        const float xd = D + g.gs, yd = D + g.ge;                                            \
+        const float X = fmaxf(fmaxf(xmq, xd), xiq);                                          \
+        const float Y = fmaxf(fmaxf(ymq, yd), yiq);                                          \
+        const float Z = fmaxf(zmq, ziq);                                                     \
+        or_if_eq(acc[q][0], xmq, X, bm, one);                                                \
+        or_if_eq(acc[q][1], xd, X, bm, one);                                                 \
+        or_if_eq(acc[q][2], ymq, Y, bm, one);                                                \
+        or_if_eq(acc[q][3], yd, Y, bm, one);                                                 \
+        or_if_gt(acc[q][4], zmq, ziq, bm, one);                                              \
+        Xp[q] = X;                                                                           \
+        Zp[q] = Z;                                                                           \
+        D = Y;                                                                               \
+    }
+
+template <int R>
+__global__ void __launch_bounds__(PIPE_WARPS * 32)
+viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+                     unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
+                     const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
+                     float4* __restrict__ bnd_all, uint32_t bnd_stride, uint8_t* __restrict__ dirs,
+                     PairResult* __restrict__ results) {
+    static_assert(R % 2 == 0, "rows are processed in pairs");
+    constexpr int R4 = (R + 3) / 4;
+    constexpr int H = 32 * R;
+    constexpr uint32_t WPL = (5 * R + 3) & ~3u;
+    extern __shared__ float4 s_dyn[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* s_tab = s_dyn + (size_t)warp * R4 * 16 * 32;
+    float2* bnd = reinterpret_cast<float2*>(bnd_all + ((size_t)blockIdx.x * PIPE_WARPS + warp) * 2 * bnd_stride);
+    const uint32_t FULL = 0xffffffffu;
+    const int rot = (lane + 31) & 31;
+    const f2 ng2 = mk2(g.ng, g.ng), go2 = mk2(g.go, g.go), gs2 = mk2(g.gs, g.gs), ge2 = mk2(g.ge, g.ge);
+    const char* tab_lane = reinterpret_cast<const char*>(s_tab) + lane * 16;
+    const uint32_t one = g.k;  // == 1, but opaque to the compiler: keeps the accumulate an IMAD
+
+    for(;;) {
+        uint32_t p = 0;
+        if(lane == 0) p = first + atomicAdd(counter, 1u);
+        p = __shfl_sync(FULL, p, 0);
+        if(p >= last) break;
+        const PairDesc pd = pairs[p];
+        if(results[pd.orig].status != 0 || pd.la == 0 || pd.lb == 0) continue;
+        const uint32_t la = pd.la, lb = pd.lb;
+        const uint8_t* a = a_all + pd.a_off;
+        const uint8_t* b = b_all + pd.b_off;
+        uint4* dir = reinterpret_cast<uint4*>(dirs + pd.dir_off);
+        const uint32_t nblocks = pipe_nblocks(lb);
+        const uint32_t nbands = (la + H - 1) / H;
+        const uint32_t nsteps = lb + 31;
+
+        // row above band 0 = top margin row r = 0 (align_pair.cc:88-90)
+        for(uint32_t c = 1 + lane; c <= lb; c += 32) {
+            const CellOut o = cell_out<1>(LOWEST, LOWEST, margin_ins<1>(c, g), g);
+            bnd[c] = make_float2(o.X, o.Y);
+        }
+        __syncwarp();
+
+        for(uint32_t band = 0; band < nbands; ++band) {
+            const float2* bin = bnd + (band & 1) * 2 * bnd_stride;
+            float2* bout = bnd + ((band + 1) & 1) * 2 * bnd_stride;
+            const uint32_t r0 = band * H + lane * R + 1;  // first row of this lane
+            // ---- private substitution rows: s_tab[h][nuc][lane] = rows 4h..4h+3 ---------------
+#pragma unroll
+            for(int h = 0; h < R4; ++h) {
+                float rowv[4][16];
+#pragma unroll
+                for(int x = 0; x < 4; ++x) {
+                    const uint32_t r = r0 + 4 * h + x;
+                    const bool ok = (4 * h + x < R) && r <= la;
+                    const uint32_t code = ok ? a[r - 1] : 0;
+#pragma unroll
+                    for(int n = 0; n < 16; ++n) rowv[x][n] = ok ? table[code * TABLE_LD + n] : 0.0f;
+                }
+#pragma unroll
+                for(int n = 0; n < 16; ++n)
+                    s_tab[(h * 16 + n) * 32 + lane] = make_float4(rowv[0][n], rowv[1][n], rowv[2][n], rowv[3][n]);
+            }
+            // ---- state at column 0 (left margin, align_pair.cc:84-87) -------------------------
+            float Xp[R], Zp[R], diagX;
+            uint32_t acc[R][5];
+#pragma unroll
+            for(int q = 0; q < R; ++q) {
+                Xp[q] = margin_del<1>(r0 + q, g) + g.gs;  // X(r, 0): only D is finite
+                Zp[q] = LOWEST;                           // Z(r, 0)
+#pragma unroll
+                for(int j = 0; j < 5; ++j) acc[q][j] = 0;
+            }
+            diagX = r0 == 1 ? (0.0f + g.ng) + g.ng : margin_del<1>(r0 - 1, g) + g.gs;
+            // lane 31's outgoing registers carry lane 0's inputs: row above the band + symbol
+            float outX = 0.f, outY = 0.f;
+            uint32_t boff = 0;
+            if(lane == 31) {
+                const float2 v = bin[1];
+                outX = v.x, outY = v.y;
+                boff = (uint32_t)b[0] * 512u;
+            }
+            uint32_t u = 0u - (uint32_t)lane;  // u = t - lane = c - 1
+            __syncwarp();
+
+            for(uint32_t t = 0; t < nsteps; ++t, ++u) {
+                const float recvX = __shfl_sync(FULL, outX, rot);
+                const float recvY = __shfl_sync(FULL, outY, rot);
+                const uint32_t bo = __shfl_sync(FULL, boff, rot);
+                // lane 0's inputs for the NEXT step (column t + 2), uniform addresses
+                const uint32_t cn = min(t + 2, lb);
+                const float2 bnv = bin[cn];
+                const uint32_t bl = b[cn - 1];
+                if(u < lb) {
+                    const uint32_t bm = 1u << (31 - (t & 31));
+                    float sv[R4 * 4];
+#pragma unroll
+                    for(int h = 0; h < R4; ++h) {
+                        const float4 v = *reinterpret_cast<const float4*>(tab_lane + bo + h * 8192);
+                        sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
+                    }
+                    float D = recvY, dXq = diagX;
+#pragma unroll
+                    for(int q = 0; q < R; q += 2) {
+                        const f2 M2 = add2(mk2(dXq, Xp[q]), mk2(sv[q], sv[q + 1]));
+                        const f2 I2 = mk2(Zp[q], Zp[q + 1]);
+                        const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2);
+                        const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2);
+                        dXq = Xp[q + 1];
+                        COATI_ROW(q, lo2(xm), lo2(ym), lo2(zm), lo2(xi), lo2(yi), lo2(zi))
+                        COATI_ROW(q + 1, hi2(xm), hi2(ym), hi2(zm), hi2(xi), hi2(yi), hi2(zi))
+                    }
+                    outX = Xp[R - 1];
+                    outY = D;
+                    diagX = recvX;
+                    if(lane == 31) bout[u + 1] = make_float2(outX, outY);
+                }
+                boff = bo;
+                if(lane == 31) {
+                    outX = bnv.x, outY = bnv.y;
+                    boff = bl * 512u;
+                }
+                // ---- flush the 32-step block of decision planes ---------------------------------
+                if((t & 31) == 31 || t == nsteps - 1) {
+                    uint4* dst = dir + ((size_t)(band * nblocks + (t >> 5)) * 32 + lane) * (WPL / 4);
+                    uint32_t w[WPL];
+#pragma unroll
+                    for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
+#pragma unroll
+                    for(int x = 0; x < (int)WPL / 4; ++x)
+                        dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
+#pragma unroll
+                    for(int q = 0; q < R; ++q)
+#pragma unroll
+                        for(int j = 0; j < 5; ++j) acc[q][j] = 0;
+                }
+            }
+            // Viterbi score = X(La, Lb): max3 of the adjusted terminal scores (align_pair.cc:130-138,265)
+            if(band == nbands - 1) {
+                const uint32_t rr = (la - 1) % H;
+                if((uint32_t)lane == rr / R) {
+                    float score = 0.f;
+#pragma unroll
+                    for(int q = 0; q < R; ++q)
+                        if((uint32_t)q == rr % R) score = Xp[q];
+                    results[pd.orig].score = score;
+                }
+            }
+            __syncwarp();  // bout of this band is bin of the next
+        }
+    }
+}
+
+#undef COATI_ROW
+
+}  // namespace coati_gpu
