@@ -71,6 +71,14 @@ def load_library() -> C.CDLL:
     lib.coati_synth_fill.restype = None
     lib.coati_gpu_batch_destroy.argtypes = [vp]
     lib.coati_gpu_batch_destroy.restype = None
+    lib.coati_gpu_forward.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(vp)]
+    lib.coati_gpu_forward_terminal.argtypes = [vp, _fp, _fp]
+    lib.coati_gpu_sampleback.argtypes = [vp, C.c_char_p, C.c_char_p, _u64p, C.c_size_t, vp, vp,
+                                         C.POINTER(C.c_size_t), _fp, _fp]
+    lib.coati_gpu_forward_free.argtypes = [vp]
+    lib.coati_gpu_forward_free.restype = None
+    lib.coati_gpu_forward_matrices.argtypes = [vp, _fp, _fp, _fp]
+    lib.coati_gpu_libm_eval.argtypes = [vp, C.c_int, _fp, _fp, C.c_size_t]
     lib.coati_gpu_viterbi_directions.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, _u8p, _fp]
     _LIB = lib
     return lib
@@ -163,6 +171,57 @@ class Batch:
             pass
 
 
+class Forward:
+    """Opaque Forward work object (coati_gpu_forward_t)."""
+
+    def __init__(self, ctx: "Context", a, b):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.a = np.ascontiguousarray(a, dtype=np.uint8)
+        self.b = np.ascontiguousarray(b, dtype=np.uint8)
+        self.h = C.c_void_p()
+        ctx._check(self.lib.coati_gpu_forward(ctx.h, self.a.ctypes.data_as(_u8p), len(self.a),
+                                              self.b.ctypes.data_as(_u8p), len(self.b), C.byref(self.h)))
+
+    def terminal(self):
+        term = np.zeros(3, dtype=np.float32)
+        ms = C.c_float(0)
+        self.ctx._check(self.lib.coati_gpu_forward_terminal(self.h, term.ctypes.data_as(_fp), C.byref(ms)))
+        return term, ms.value
+
+    def matrices(self):
+        shape = (len(self.a) + 1, len(self.b) + 1)
+        m, d, i = (np.empty(shape, dtype=np.float32) for _ in range(3))
+        self.ctx._check(self.lib.coati_gpu_forward_matrices(self.h, m.ctypes.data_as(_fp), d.ctypes.data_as(_fp),
+                                                            i.ctypes.data_as(_fp)))
+        return m, d, i
+
+    def sampleback(self, anc: str, des: str, state, n: int):
+        """Returns (list[(row_a, row_b)], float32 scores, new_state, sample_ms)."""
+        stride = len(self.a) + len(self.b) + 1
+        oa = np.zeros(n * stride + 1, dtype=np.uint8)
+        ob = np.zeros(n * stride + 1, dtype=np.uint8)
+        ol = (C.c_size_t * max(n, 1))()
+        sc = np.zeros(max(n, 1), dtype=np.float32)
+        st = (C.c_uint64 * 2)(int(state[0]), int(state[1]))
+        ms = C.c_float(0)
+        self.ctx._check(self.lib.coati_gpu_sampleback(self.h, anc.encode("latin-1"), des.encode("latin-1"), st, n,
+                                                      _vp(oa), _vp(ob), ol, sc.ctypes.data_as(_fp), C.byref(ms)))
+        rows = [(oa[s * stride:s * stride + ol[s]].tobytes().decode("latin-1"),
+                 ob[s * stride:s * stride + ol[s]].tobytes().decode("latin-1")) for s in range(n)]
+        return rows, sc[:n], np.array([st[0], st[1]], dtype=np.uint64), ms.value
+
+    def free(self):
+        if self.h:
+            self.lib.coati_gpu_forward_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU context (coati_gpu_ctx).  Raises CoatiGpuError on any failure -- never falls back."""
 
@@ -239,6 +298,15 @@ class Context:
             rows_a.append(out_a[o:o + n].tobytes().decode("latin-1"))
             rows_b.append(out_b[o:o + n].tobytes().decode("latin-1"))
         return rows_a, rows_b, score, status
+
+    def forward(self, a, b) -> "Forward":
+        return Forward(self, a, b)
+
+    def libm_eval(self, op: int, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self._check(self.lib.coati_gpu_libm_eval(self.h, op, x.ctypes.data_as(_fp), out.ctypes.data_as(_fp), x.size))
+        return out
 
     def batch(self, a_off, b_off) -> Batch:
         return Batch(self, a_off, b_off)

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "forward.cuh"
 #include "traceback.cuh"
 #include "viterbi_generic.cuh"
 #include "viterbi_pipe.cuh"
@@ -742,4 +743,187 @@ extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a
     if(rc == COATI_GPU_OK && score) *score = sc;
     coati_gpu_batch_destroy(bt);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward fill + sampleback (one pair per handle)
+struct coati_gpu_forward_t {
+    coati_gpu_ctx* ctx = nullptr;
+    uint32_t la = 0, lb = 0;
+    DevBuf<uint8_t> d_a, d_b;
+    DevBuf<char> d_anc, d_des, d_out_a, d_out_b;
+    DevBuf<FwdDesc> d_desc;
+    DevBuf<float> d_mats, d_term, d_scores;
+    DevBuf<uint64_t> d_rng, d_out_off;
+    DevBuf<uint32_t> d_len, d_start;
+    DevBuf<int32_t> d_status;
+    float term[3] = {0, 0, 0};
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float fill_ms = 0, sample_ms = 0;
+    ~coati_gpu_forward_t() {
+        for(cudaEvent_t e : ev)
+            if(e) cudaEventDestroy(e);
+    }
+};
+
+extern "C" int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
+                                 size_t Lb, coati_gpu_forward_t** out) {
+    if(!ctx || !out || !ctx->model_set || (La && !a) || (Lb && !b)) return COATI_GPU_E_ARG;
+    *out = nullptr;
+    if(La > 0x7fffffffull || Lb > 0x7fffffffull) return COATI_GPU_E_ARG;
+    if(La % ctx->gap.k != 0 || Lb % ctx->gap.k != 0) return COATI_GPU_E_LENGTH;
+    for(size_t x = 0; x < La; ++x)
+        if(a[x] >= TABLE_ROWS) return COATI_GPU_E_SYMBOL;
+    for(size_t x = 0; x < Lb; ++x)
+        if(b[x] >= TABLE_COLS) return COATI_GPU_E_SYMBOL;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<coati_gpu_forward_t> h(new(std::nothrow) coati_gpu_forward_t);
+    if(!h) return COATI_GPU_E_NOMEM;
+    h->ctx = ctx;
+    h->la = (uint32_t)La;
+    h->lb = (uint32_t)Lb;
+    const uint64_t plane = (uint64_t)(La + 1) * (Lb + 1);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) {
+        if(e == cudaSuccess) e = r;
+    };
+    ok(h->d_a.alloc(La + 1, &ctx->pool));
+    ok(h->d_b.alloc(Lb + 1, &ctx->pool));
+    ok(h->d_desc.alloc(1, &ctx->pool));
+    ok(h->d_mats.alloc(3 * plane, &ctx->pool));
+    ok(h->d_term.alloc(4, &ctx->pool));
+    if(e != cudaSuccess) {
+        ctx->last_error = std::string("forward allocation: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return COATI_GPU_E_NOMEM;
+    }
+    for(cudaEvent_t& ev : h->ev) CU_TRY(ctx, cudaEventCreate(&ev));
+    cudaStream_t s = ctx->stream;
+    FwdDesc fd{0, 0, 0, (uint32_t)La, (uint32_t)Lb};
+    CU_TRY(ctx, cudaMemcpyAsync(h->d_desc.p, &fd, sizeof(fd), cudaMemcpyHostToDevice, s));
+    if(La) CU_TRY(ctx, cudaMemcpyAsync(h->d_a.p, a, La, cudaMemcpyHostToDevice, s));
+    if(Lb) CU_TRY(ctx, cudaMemcpyAsync(h->d_b.p, b, Lb, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaEventRecord(h->ev[0], s));
+    forward_fill_kernel<<<1, 256, 0, s>>>(h->d_desc.p, 1, h->d_a.p, h->d_b.p, ctx->d_table, ctx->gap,
+                                          h->d_mats.p, h->d_term.p);
+    ++ctx->launches;
+    CU_TRY(ctx, cudaEventRecord(h->ev[1], s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->term, h->d_term.p, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventElapsedTime(&h->fill_ms, h->ev[0], h->ev[1]));
+    *out = h.release();
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_forward_terminal(coati_gpu_forward_t* h, float term[3], float* fill_ms) {
+    if(!h) return COATI_GPU_E_ARG;
+    if(term)
+        for(int x = 0; x < 3; ++x) term[x] = h->term[x];
+    if(fill_ms) *fill_ms = h->fill_ms;
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_forward_matrices(coati_gpu_forward_t* h, float* mch, float* del, float* ins) {
+    if(!h || !mch || !del || !ins) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = h->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t plane = (uint64_t)(h->la + 1) * (h->lb + 1);
+    cudaStream_t s = ctx->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(mch, h->d_mats.p, plane * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(del, h->d_mats.p + plane, plane * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(ins, h->d_mats.p + 2 * plane, plane * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_sampleback(coati_gpu_forward_t* h, const char* anc, const char* des,
+                                    uint64_t rng_state[2], size_t n, char* out_a, char* out_b,
+                                    size_t* out_len, float* scores, float* sample_ms) {
+    if(!h || !rng_state || (n && (!out_a || !out_b))) return COATI_GPU_E_ARG;
+    if((h->la && !anc) || (h->lb && !des) || n > 0x7fffffffull) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = h->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t stride = (size_t)h->la + h->lb + 1;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) {
+        if(e == cudaSuccess) e = r;
+    };
+    ok(h->d_anc.alloc(h->la + 1, &ctx->pool));
+    ok(h->d_des.alloc(h->lb + 1, &ctx->pool));
+    ok(h->d_out_a.alloc(n * stride + 1, &ctx->pool));
+    ok(h->d_out_b.alloc(n * stride + 1, &ctx->pool));
+    ok(h->d_rng.alloc(2, &ctx->pool));
+    ok(h->d_out_off.alloc(1, &ctx->pool));
+    ok(h->d_len.alloc(n + 1, &ctx->pool));
+    ok(h->d_start.alloc(n + 1, &ctx->pool));
+    ok(h->d_scores.alloc(n + 1, &ctx->pool));
+    ok(h->d_status.alloc(1, &ctx->pool));
+    if(e != cudaSuccess) {
+        ctx->last_error = std::string("sampleback allocation: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return COATI_GPU_E_NOMEM;
+    }
+    const uint64_t zero = 0;
+    const uint64_t st[2] = {rng_state[0] | 1ull, rng_state[1]};  // Lehmer64Fast::SetState (random.hpp:131-134)
+    if(h->la) CU_TRY(ctx, cudaMemcpyAsync(h->d_anc.p, anc, h->la, cudaMemcpyHostToDevice, s));
+    if(h->lb) CU_TRY(ctx, cudaMemcpyAsync(h->d_des.p, des, h->lb, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->d_rng.p, st, sizeof(st), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->d_out_off.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaEventRecord(h->ev[1], s));
+    sampleback_kernel<<<1, 32, 0, s>>>(h->d_desc.p, 1, h->d_mats.p, h->d_term.p, ctx->d_table, h->d_a.p,
+                                       h->d_b.p, h->d_anc.p, h->d_des.p, ctx->gap, h->d_rng.p,
+                                       (uint32_t)n, h->d_out_off.p, h->d_out_a.p, h->d_out_b.p,
+                                       h->d_len.p, h->d_start.p, h->d_scores.p, h->d_status.p);
+    if(n) {
+        compact_samples_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(
+            h->d_desc.p, 1, (uint32_t)n, h->d_out_off.p, h->d_out_a.p, h->d_out_b.p, h->d_len.p,
+            h->d_start.p);
+    }
+    ctx->launches += 2;
+    CU_TRY(ctx, cudaEventRecord(h->ev[2], s));
+    std::vector<uint32_t> lens(n);
+    uint64_t st_out[2] = {0, 0};
+    int32_t status = 0;
+    if(n) {
+        CU_TRY(ctx, cudaMemcpyAsync(out_a, h->d_out_a.p, n * stride, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(out_b, h->d_out_b.p, n * stride, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(lens.data(), h->d_len.p, n * 4, cudaMemcpyDeviceToHost, s));
+        if(scores) CU_TRY(ctx, cudaMemcpyAsync(scores, h->d_scores.p, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(st_out, h->d_rng.p, sizeof(st_out), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(&status, h->d_status.p, sizeof(status), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventElapsedTime(&h->sample_ms, h->ev[1], h->ev[2]));
+    if(sample_ms) *sample_ms = h->sample_ms;
+    if(out_len)
+        for(size_t x = 0; x < n; ++x) out_len[x] = lens[x];
+    rng_state[0] = st_out[0];
+    rng_state[1] = st_out[1];
+    return status;
+}
+
+extern "C" void coati_gpu_forward_free(coati_gpu_forward_t* h) {
+    if(!h) return;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    delete h;
+}
+
+extern "C" int coati_gpu_libm_eval(coati_gpu_ctx* ctx, int op, const float* in, float* out, size_t n) {
+    if(!ctx || !in || !out || op < 0 || op > 3) return COATI_GPU_E_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf<float> d_in, d_out;
+    if(d_in.alloc(n + 1, &ctx->pool) != cudaSuccess || d_out.alloc(n + 1, &ctx->pool) != cudaSuccess)
+        return COATI_GPU_E_NOMEM;
+    cudaStream_t s = ctx->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(d_in.p, in, n * 4, cudaMemcpyHostToDevice, s));
+    libm_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(op, d_in.p, d_out.p, n);
+    ++ctx->launches;
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    CU_TRY(ctx, cudaGetLastError());
+    return COATI_GPU_OK;
 }

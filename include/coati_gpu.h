@@ -115,6 +115,30 @@ void coati_synth_fill(uint64_t seed, uint64_t first, uint64_t n, int workload, d
                       double indel, int threads, const uint64_t* a_off, const uint64_t* b_off,
                       char* anc_all, char* des_all, uint8_t* a_all, uint8_t* b_all);
 
+/* ---- Forward fill + seeded stochastic sampleback ----------------------------------------------
+ * coati_gpu_forward   = forward (align_pair.cc:149-152: forward_impl<semiring::log, align_pair_work_t>).
+ *                       The handle owns the device-resident state matrices (opaque work object: no
+ *                       caller of the reference ever reads align_pair_work_t).
+ * coati_gpu_sampleback = n consecutive sampleback calls (align_pair.cc:401-458) on one RNG stream, as
+ *                       marg_sample's loop does (align_marginal.cc:589-593).  rng_state is the raw
+ *                       128-bit Lehmer64Fast state {low, high 64 bits} (random.hpp:99,115 GetState /
+ *                       Seed(state_type)), in-out, so a host `Random` stays in lock-step.
+ *                       out_a/out_b: n rows of stride La+Lb+1 bytes, NUL-terminated; scores[n].
+ * coati_gpu_forward_terminal: the adjusted terminal M, D, I (align_pair.cc:130-138); the forward
+ *                       log-likelihood is log_sum_exp of the three. */
+int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b, size_t Lb,
+                      coati_gpu_forward_t** handle);
+int coati_gpu_forward_terminal(coati_gpu_forward_t* handle, float term[3], float* fill_ms);
+int coati_gpu_sampleback(coati_gpu_forward_t* handle, const char* anc, const char* des,
+                         uint64_t rng_state[2], size_t n, char* out_a, char* out_b, size_t* out_len,
+                         float* scores, float* sample_ms);
+void coati_gpu_forward_free(coati_gpu_forward_t* handle);
+/* parity aids: the three state matrices in lattice coordinates, (La+1) x (Lb+1) row-major (the
+ * reference's (La+k) x (Lb+k) matrices without their k-1 padding rows/columns); and the device
+ * twins of libm (op 0: expf, 1: logf, 2: log1pf, 3: log1p_exp of utils.hpp:134-146) on an array. */
+int coati_gpu_forward_matrices(coati_gpu_forward_t* handle, float* mch, float* del, float* ins);
+int coati_gpu_libm_eval(coati_gpu_ctx* ctx, int op, const float* in, float* out, size_t n);
+
 /* ---- debugging / parity aid -------------------------------------------------------------------
  * Fill one pair and return the decision byte of every body cell, row-major La x Lb
  * (bits 0-1: next state after a MATCH step lands on the cell, bits 2-3: after a DELETION step,
