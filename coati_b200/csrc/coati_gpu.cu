@@ -87,7 +87,8 @@ struct coati_gpu_ctx {
     uint64_t launches = 0;
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
-    bool force_generic = false;
+    bool force_generic = false, no_wave = false;
+    uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
     DevPool pool;
 };
 
@@ -146,24 +147,37 @@ struct Run {
 typedef void (*pipe_kernel_t)(const PairDesc*, uint32_t, uint32_t, unsigned int*, const uint8_t*,
                               const uint8_t*, const float*, GapConsts, float4*, uint32_t, uint8_t*,
                               PairResult*);
+typedef void (*pipe1_kernel_t)(const PairDesc*, uint32_t, uint32_t, unsigned int*, const uint8_t*,
+                               const uint8_t*, const float*, GapConsts, float4*, uint32_t, uint8_t*,
+                               PairResult*, uint32_t*);
 struct PipeCfg {
     uint32_t k, R;
-    pipe_kernel_t fn;
+    bool wave;
+    pipe_kernel_t fn;    // generic-K pipelined kernel (viterbi_pipe.cuh)
+    pipe1_kernel_t fn1;  // K = 1 specialisation (viterbi_pipe1.cuh); takes precedence when set
     size_t smem;
     int ctas_per_sm;
+    const void* entry() const { return fn1 ? (const void*)fn1 : (const void*)fn; }
 };
 template <int K, int R>
 PipeCfg make_cfg() {
-    return PipeCfg{(uint32_t)K, (uint32_t)R, viterbi_pipe_kernel<K, R>,
+    return PipeCfg{(uint32_t)K, (uint32_t)R, false, viterbi_pipe_kernel<K, R>, nullptr,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
 }
-template <int R>
-PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation (viterbi_pipe1.cuh)
-    PipeCfg c = make_cfg<1, R>();
-    c.fn = viterbi_pipe1_kernel<R>;
-    return c;
+template <int R, bool WAVE>
+PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false) or intra-pair wavefront
+    return PipeCfg{1u, (uint32_t)R, WAVE, nullptr, viterbi_pipe1_kernel<R, WAVE>,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
 }
-PipeCfg g_pipe_cfgs[] = {make_cfg1<4>(), make_cfg1<8>(), make_cfg<3, 3>(), make_cfg<3, 6>()};
+PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false>(), make_cfg1<8, false>(), make_cfg<3, 3>(),
+                         make_cfg<3, 6>(),      make_cfg1<2, true>(),  make_cfg1<4, true>(),
+                         make_cfg1<8, true>()};
+
+const PipeCfg* find_cfg(uint32_t k, uint32_t cfg) {
+    for(const PipeCfg& pc : g_pipe_cfgs)
+        if(pc.k == k && pc.R == (cfg & 0xffu) && pc.wave == ((cfg & CFG_WAVE) != 0)) return &pc;
+    return nullptr;
+}
 
 // issue-slot model of one pair on one warp: bands x steps x (R cells + per-step overhead)
 double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
@@ -189,6 +203,7 @@ struct coati_gpu_batch {
     DevBuf<unsigned int> d_counters;
     DevBuf<float> d_ring;
     DevBuf<float4> d_bnd;
+    DevBuf<uint32_t> d_prog;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
     std::vector<PairResult> h_results;
     std::vector<cudaEvent_t> events;  // 4 per run: fill start, fill end, traceback end, compact end
@@ -240,15 +255,20 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     if(const char* env = std::getenv("COATI_GPU_FORCE_GENERIC")) ctx->force_generic = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_PIPE_SCALAR")) {  // A/B: scalar template for K = 1
         if(env[0] == '1') {
-            g_pipe_cfgs[0].fn = viterbi_pipe_kernel<1, 4>;
-            g_pipe_cfgs[1].fn = viterbi_pipe_kernel<1, 8>;
+            g_pipe_cfgs[0].fn = viterbi_pipe_kernel<1, 4>, g_pipe_cfgs[0].fn1 = nullptr;
+            g_pipe_cfgs[1].fn = viterbi_pipe_kernel<1, 8>, g_pipe_cfgs[1].fn1 = nullptr;
         }
     }
+    if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_WAVE_R")) {
+        const uint32_t r = (uint32_t)std::atoi(env);
+        if(r == 2 || r == 4 || r == 8) ctx->wave_r = r;
+    }
     for(PipeCfg& pc : g_pipe_cfgs) {
-        if(cudaFuncSetAttribute(pc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem) !=
-               cudaSuccess ||
-           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pc.ctas_per_sm, pc.fn, PIPE_WARPS * 32,
-                                                         pc.smem) != cudaSuccess ||
+        if(cudaFuncSetAttribute(pc.entry(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)pc.smem) != cudaSuccess ||
+           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pc.ctas_per_sm, pc.entry(),
+                                                         PIPE_WARPS * 32, pc.smem) != cudaSuccess ||
            pc.ctas_per_sm < 1) {
             cudaGetLastError();
             coati_gpu_shutdown(ctx);
@@ -372,9 +392,21 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
         if(!ctx->force_generic && la > 0 && lb > 0) {
             double best = 0;
             for(const PipeCfg& pc : g_pipe_cfgs) {
-                if(pc.k != k) continue;
+                if(pc.k != k || pc.wave) continue;
                 const double c = pipe_cost(d.la, d.lb, pc.R);
                 if(d.cfg == 0 || c < best) best = c, d.cfg = pc.R;
+            }
+            // long pairs (or pairs of a batch too small to fill the GPU) run as an intra-pair wavefront
+            const uint64_t cells = la * lb;
+            const bool small_batch = npairs < 2048;
+            if(k == 1 && !ctx->no_wave && la >= 1024 && lb >= 512 &&
+               (cells >= (1ull << 26) || (small_batch && cells >= (1ull << 21)))) {
+                const uint64_t nb8 = (la + 255) / 256, nb4 = (la + 127) / 128;
+                // measured on B200 (tools/wave_exp.py): the systolic chain is latency bound per step, so
+                // the widest lane tile wins at every length from 10k to 160k
+                (void)nb8, (void)nb4;
+                d.cfg = 8u | CFG_WAVE;
+                if(ctx->wave_r) d.cfg = ctx->wave_r | CFG_WAVE;
             }
         }
         // the reference checks divisibility before trimming stops (utils.cc:819-837); a lattice
@@ -404,7 +436,7 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
             const bool live = bt->host_status[d.orig] == COATI_GPU_OK;
             const uint64_t cells = live ? (uint64_t)d.la * d.lb : 0;
             const uint64_t bytes = !live || cells == 0 ? 0
-                                   : d.cfg ? pipe_dir_bytes(d.la, d.lb, d.cfg) : cells;
+                                   : d.cfg ? pipe_dir_bytes(d.la, d.lb, d.cfg & 0xffu) : cells;
             const uint64_t padded = (bytes + 127) & ~127ull;
             if(padded > budget) {
                 ctx->last_error = "direction stream of one pair exceeds device memory budget";
@@ -431,7 +463,8 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
         const Chunk& c = bt->chunks[ci];
         uint32_t s0 = c.first;
         for(uint32_t s = c.first; s <= c.last; ++s) {
-            if(s == c.last || bt->descs[s].cfg != bt->descs[s0].cfg) {
+            if(s == c.last || bt->descs[s].cfg != bt->descs[s0].cfg ||
+               (bt->descs[s0].cfg & CFG_WAVE)) {
                 if(s > s0) bt->runs.push_back(Run{s0, s, bt->descs[s0].cfg, (uint32_t)ci});
                 s0 = s;
             }
@@ -440,14 +473,22 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     }
     bt->bnd_stride = (max_lb_pipe + 2 + 7) & ~7u;
     bt->bnd_ctas = 0;
+    uint64_t wave_f4 = 0;
+    uint32_t wave_bands = 0;
     for(const Run& r : bt->runs) {
         if(!r.cfg) continue;
-        for(const PipeCfg& pc : g_pipe_cfgs)
-            if(pc.k == k && pc.R == r.cfg) {
-                const uint32_t want = (r.last - r.first + PIPE_WARPS - 1) / PIPE_WARPS;
-                const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc.ctas_per_sm;
-                bt->bnd_ctas = std::max(bt->bnd_ctas, std::min(want, cap));
-            }
+        const PipeCfg* pc = find_cfg(k, r.cfg);
+        if(!pc) return COATI_GPU_E_ARG;
+        if(r.cfg & CFG_WAVE) {
+            const PairDesc& d = bt->descs[r.first];
+            const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
+            wave_bands = std::max(wave_bands, nb);
+            wave_f4 = std::max<uint64_t>(wave_f4, (uint64_t)(nb + 1) * ((d.lb + 4) / 2));
+        } else {
+            const uint32_t want = (r.last - r.first + PIPE_WARPS - 1) / PIPE_WARPS;
+            const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
+            bt->bnd_ctas = std::max(bt->bnd_ctas, std::min(want, cap));
+        }
     }
     // device buffers
     uint32_t max_la = 0, n_generic = 0;
@@ -472,7 +513,9 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     ok(bt->d_pairs.alloc(npairs + 1, &ctx->pool));
     ok(bt->d_results.alloc(npairs + 1, &ctx->pool));
     ok(bt->d_counters.alloc(bt->runs.size() + 1, &ctx->pool));
-    ok(bt->d_bnd.alloc((size_t)bt->bnd_ctas * PIPE_WARPS * 2 * bt->bnd_stride, &ctx->pool));
+    ok(bt->d_bnd.alloc(std::max<uint64_t>((uint64_t)bt->bnd_ctas * PIPE_WARPS * 2 * bt->bnd_stride, wave_f4),
+                       &ctx->pool));
+    ok(bt->d_prog.alloc(wave_bands ? wave_bands + 2 : 0, &ctx->pool));
     ok(bt->d_dirs.alloc(need_max + 128, &ctx->pool));
     ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride, &ctx->pool));
     if(e != cudaSuccess) {
@@ -551,25 +594,57 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                         bt->ring_stride, bt->d_dirs.p,
                                                         bt->d_results.p);
             cudaEventRecord(ev[1], s);
-            traceback_kernel<DiagLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
+            traceback_kernel<DiagLayout, false><<<(cnt + 63) / 64, 64, 0, s>>>(
                 bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
                 bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
         } else {
-            const PipeCfg* pc = nullptr;
-            for(const PipeCfg& x : g_pipe_cfgs)
-                if(x.k == ctx->gap.k && x.R == r.cfg) pc = &x;
+            const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg);
             if(!pc) return COATI_GPU_E_ARG;
-            const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
-            const uint32_t grid = std::min(
-                want, std::min(bt->bnd_ctas,
-                               (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm));
-            pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
-                bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p, bt->d_results.p);
+            const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
+            if(pc->wave) {
+                const PairDesc& d = bt->descs[r.first];
+                const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
+                const uint32_t grid = std::min((nb + PIPE_WARPS - 1) / PIPE_WARPS, cap);
+                // NaN sentinel in every boundary entry: the data is its own ready flag
+                CU_TRY(ctx, cudaMemsetAsync(bt->d_bnd.p, 0xff,
+                                            (size_t)(nb + 1) * ((d.lb + 4) / 2) * sizeof(float4), s));
+                pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
+                    bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                    ctx->d_table, ctx->gap, bt->d_bnd.p, (d.lb + 4) / 2, bt->d_dirs.p,
+                    bt->d_results.p, bt->d_prog.p);
+            } else {
+                const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
+                const uint32_t grid = std::min(want, std::min(bt->bnd_ctas, cap));
+                if(pc->fn1)
+                    pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
+                        bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                        ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
+                        bt->d_results.p, nullptr);
+                else
+                    pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
+                        bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                        ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
+                        bt->d_results.p);
+            }
             cudaEventRecord(ev[1], s);
-            traceback_kernel<PipeLayout><<<(cnt + 63) / 64, 64, 0, s>>>(
-                bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
-                bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+#define COATI_TB(RR)                                                                                   \
+    if(pc->wave)                                                                                       \
+        traceback_kernel<PipeLayoutR<RR>, true><<<cnt, 32, 0, s>>>(                                    \
+            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,          \
+            bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);                                            \
+    else                                                                                               \
+        traceback_kernel<PipeLayoutR<RR>, false><<<(cnt + 63) / 64, 64, 0, s>>>(                       \
+            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,          \
+            bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+            switch(pc->R) {
+            case 2: COATI_TB(2) break;
+            case 3: COATI_TB(3) break;
+            case 4: COATI_TB(4) break;
+            case 6: COATI_TB(6) break;
+            case 8: COATI_TB(8) break;
+            default: return COATI_GPU_E_ARG;
+            }
+#undef COATI_TB
         }
         cudaEventRecord(ev[2], s);
         compact_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last,

@@ -40,8 +40,12 @@ struct PairDesc {
     uint64_t out_off;  // into out_a / out_b (capacity la + lb + 1)
     uint32_t la, lb;
     uint32_t orig;     // index in caller order
-    uint32_t cfg;      // 0: generic-k kernel (DiagLayout); else rows per lane R of the pipelined kernel
+    uint32_t cfg;      // 0: generic-k kernel (DiagLayout); else rows per lane R of the pipelined
+                       // kernel, | CFG_WAVE when the pair runs as an intra-pair wavefront
+
 };
+
+constexpr uint32_t CFG_WAVE = 0x100u;
 
 // Per-pair results (device side, caller order).
 struct PairResult {

@@ -12,6 +12,10 @@ namespace coati_gpu {
 
 // Generic-k kernels: one decision byte per body cell, anti-diagonal-major (common.cuh).
 struct DiagLayout {
+    __device__ __forceinline__ static uint32_t touch(const uint8_t* dir, const PairDesc& pd, uint32_t r,
+                                                     uint32_t c) {
+        return dir[dir_index_diag(r, c, pd.la, pd.lb)];
+    }
     __device__ __forceinline__ static int initial(const uint8_t*, const PairDesc&, PairResult& res) {
         const float tM = res.term[0], tD = res.term[1], tI = res.term[2];
         res.score = fmaxf(fmaxf(tM, tD), tI);  // align_pair.cc:265
@@ -24,23 +28,39 @@ struct DiagLayout {
     }
 };
 
-// Pipelined kernels: five bit-planes per row (viterbi_pipe.cuh).  pd.cfg = R.
-struct PipeLayout {
-    __device__ __forceinline__ static uint32_t plane_bit(const uint32_t* w, const PairDesc& pd,
-                                                         uint32_t r, uint32_t c, uint32_t plane) {
-        const uint32_t R = pd.cfg, H = 32 * R, wpl = (5 * R + 3) & ~3u;
+// Pipelined kernels: five bit-planes per row (viterbi_pipe.cuh).  R (= pd.cfg & 0xff) is a template
+// constant so the index arithmetic of the serial walk is shifts and masks, not integer divisions.
+template <int R>
+struct PipeLayoutR {
+    static constexpr uint32_t H = 32 * R, WPL = (5 * R + 3) & ~3u;
+    __device__ __forceinline__ static uint64_t word_index(const PairDesc& pd, uint32_t r, uint32_t c,
+                                                          uint32_t& shift) {
         const uint32_t band = (r - 1) / H, rr = (r - 1) % H, lane = rr / R, q = rr % R;
         const uint32_t t = (c - 1) + lane, nblocks = (pd.lb + 62) / 32;
-        const uint64_t idx = ((uint64_t)(band * nblocks + (t >> 5)) * 32 + lane) * wpl + q * 5 + plane;
-        return (w[idx] >> (31 - (t & 31))) & 1u;
+        shift = 31 - (t & 31);
+        return ((uint64_t)(band * nblocks + (t >> 5)) * 32 + lane) * WPL + q * 5;
     }
     __device__ __forceinline__ static int next(const uint8_t* dir, const PairDesc& pd, int st,
                                                uint32_t r, uint32_t c) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(dir);
-        if(st == ST_I) return plane_bit(w, pd, r, c, 4) ? ST_M : ST_I;
+        uint32_t sh;
+        const uint64_t idx = word_index(pd, r, c, sh);
+        if(st == ST_I) return ((__ldg(w + idx + 4) >> sh) & 1u) ? ST_M : ST_I;
         const uint32_t base = st == ST_M ? 0 : 2;
-        if(plane_bit(w, pd, r, c, base)) return ST_M;
-        return plane_bit(w, pd, r, c, base + 1) ? ST_D : ST_I;
+        const uint32_t w0 = __ldg(w + idx + base), w1 = __ldg(w + idx + base + 1);  // independent loads
+        if((w0 >> sh) & 1u) return ST_M;
+        return ((w1 >> sh) & 1u) ? ST_D : ST_I;
+    }
+    // touch the cache lines holding the decisions of cell (r, c) (warp-cooperative read-ahead)
+    __device__ __forceinline__ static uint32_t touch(const uint8_t* dir, const PairDesc& pd, uint32_t r,
+                                                     uint32_t c) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(dir);
+        uint32_t sh;
+        const uint64_t idx = word_index(pd, r, c, sh) - ((r - 1) % R) * 5;  // start of the lane's block
+        uint32_t v = __ldg(w + idx + WPL - 1);
+#pragma unroll
+        for(uint32_t x = 0; x < WPL; x += 8) v ^= __ldg(w + idx + x);  // L1 fills 32-byte sectors
+        return v;
     }
     // score = X(La, Lb) was written by the fill; max_mdi of the adjusted terminal scores is the
     // MATCH-lands decision of the terminal cell (align_pair.cc:130-138, 265-266).
@@ -50,15 +70,37 @@ struct PipeLayout {
     }
 };
 
-// One thread per pair.  Rows are written right-aligned into the pair's output slot
-// [out_off, out_off + la + lb]; compact_rows_kernel moves them to the front afterwards.
-template <class Layout>
+// run-time R (debug unpack path only)
+struct PipeLayout {
+    __device__ __forceinline__ static int next(const uint8_t* dir, const PairDesc& pd, int st,
+                                               uint32_t r, uint32_t c) {
+        switch(pd.cfg & 0xffu) {
+        case 2: return PipeLayoutR<2>::next(dir, pd, st, r, c);
+        case 3: return PipeLayoutR<3>::next(dir, pd, st, r, c);
+        case 4: return PipeLayoutR<4>::next(dir, pd, st, r, c);
+        case 6: return PipeLayoutR<6>::next(dir, pd, st, r, c);
+        default: return PipeLayoutR<8>::next(dir, pd, st, r, c);
+        }
+    }
+};
+
+// WARP = false: one thread per pair (batches: thousands of independent walks hide the latency).
+// WARP = true : one warp per pair (long pairs): every lane runs the same walk (uniform loads), lane 0
+//               writes the rows, and every 8 steps lane j reads ahead the decision words the path
+//               reaches in 64 + 8j steps if it keeps to its diagonal, so the serial walk finds its
+//               words in L1/L2 instead of paying a DRAM round trip per step.
+// Rows are written right-aligned into the pair's output slot [out_off, out_off + la + lb];
+// compact_rows_kernel moves them to the front afterwards.
+template <class Layout, bool WARP>
 __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                                  const uint8_t* __restrict__ dirs, const char* __restrict__ anc_all,
                                  const char* __restrict__ des_all, GapConsts gap,
                                  char* __restrict__ out_a, char* __restrict__ out_b,
                                  PairResult* __restrict__ results) {
-    const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = first + (WARP ? gtid >> 5 : gtid);
+    const uint32_t lane = WARP ? (threadIdx.x & 31) : 0;
+    const bool lead = lane == 0;
     if(p >= last) return;
     const PairDesc pd = pairs[p];
     PairResult& res = results[pd.orig];
@@ -89,27 +131,38 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
         st = Layout::initial(dir, pd, res);
     }
     int err = 0;
+    uint32_t nstep = 0, sink = 0;
     while(r > 0 || c > 0) {  // :268  (j > k-1 || i > k-1)
+        if(WARP && (nstep++ & 7) == 0) {
+            const uint32_t ahead = 64 + 8 * lane;
+            if(r > ahead && c > ahead) sink ^= Layout::touch(dir, pd, r - ahead, c - ahead);
+        }
         if(st == ST_M) {
             if(r == 0 || c == 0) { err = 1; break; }
             --pos;
-            oa[pos] = anc[r - 1];
-            ob[pos] = des[c - 1];
+            if(lead) {
+                oa[pos] = anc[r - 1];
+                ob[pos] = des[c - 1];
+            }
             --r, --c;
         } else if(st == ST_D) {
             if(r < k) { err = 1; break; }
             for(uint32_t q = 0; q < k; ++q) {
                 --pos;
-                oa[pos] = anc[r - 1 - q];
-                ob[pos] = '-';
+                if(lead) {
+                    oa[pos] = anc[r - 1 - q];
+                    ob[pos] = '-';
+                }
             }
             r -= k;
         } else {
             if(c < k) { err = 1; break; }
             for(uint32_t q = 0; q < k; ++q) {
                 --pos;
-                oa[pos] = '-';
-                ob[pos] = des[c - 1 - q];
+                if(lead) {
+                    oa[pos] = '-';
+                    ob[pos] = des[c - 1 - q];
+                }
             }
             c -= k;
         }
@@ -119,6 +172,10 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
         else if(c == 0) nst = ST_D;   // only del(i, start) is finite on the left margin (:84-87)
         else nst = Layout::next(dir, pd, st, r, c);
         st = nst;
+    }
+    if(!lead) {
+        if(sink == 0x9e3779b9u) res.pad = sink;  // keeps the read-ahead loads alive; never true in practice
+        return;
     }
     if(err) {
         res.status = -8;  // COATI_GPU_E_INTERNAL

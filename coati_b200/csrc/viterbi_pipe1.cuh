@@ -67,13 +67,31 @@ __device__ __forceinline__ void or_if_gt(uint32_t& acc, float a, float b, uint32
         D = Y;                                                                               \
     }
 
-template <int R>
+// WAVE = false: inter-pair scheme, one warp per pair, bands of a pair processed one after another by
+//                the same warp (pairs [first, last) pulled from `counter`).
+// WAVE = true : intra-pair scheme for long pairs: the kernel works on the single pair `first`; every
+//                warp of the grid pulls BANDS from `counter`, so the bands of one lattice run
+//                concurrently as a systolic wavefront across the whole GPU.  Band b reads the row
+//                above it from wave_bnd[b] and writes its bottom row to wave_bnd[b + 1].  The rows
+//                are pre-filled with a NaN sentinel and every entry is one aligned 64-bit store, so
+//                the data is its own ready flag: the consumer re-reads (L2, relaxed) until the
+//                sentinel is gone -- no flags, no fences on the producer's critical path.  Tickets
+//                are issued in band order and the grid is fully resident, so a waiting band's
+//                producer is always running.
+__device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
+    float2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+constexpr uint32_t WAVE_BLOCK = 32;  // columns of the row above fetched per refill (one per lane)
+
+template <int R, bool WAVE>
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
                      float4* __restrict__ bnd_all, uint32_t bnd_stride, uint8_t* __restrict__ dirs,
-                     PairResult* __restrict__ results) {
+                     PairResult* __restrict__ results, uint32_t* __restrict__ prog) {
     static_assert(R % 2 == 0, "rows are processed in pairs");
     constexpr int R4 = (R + 3) / 4;
     constexpr int H = 32 * R;
@@ -82,6 +100,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* s_tab = s_dyn + (size_t)warp * R4 * 16 * 32;
     float2* bnd = reinterpret_cast<float2*>(bnd_all + ((size_t)blockIdx.x * PIPE_WARPS + warp) * 2 * bnd_stride);
+    (void)prog;
     const uint32_t FULL = 0xffffffffu;
     const int rot = (lane + 31) & 31;
     const f2 ng2 = mk2(g.ng, g.ng), go2 = mk2(g.go, g.go), gs2 = mk2(g.gs, g.gs), ge2 = mk2(g.ge, g.ge);
@@ -89,12 +108,17 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     const uint32_t one = g.k;  // == 1, but opaque to the compiler: keeps the accumulate an IMAD
 
     for(;;) {
-        uint32_t p = 0;
-        if(lane == 0) p = first + atomicAdd(counter, 1u);
-        p = __shfl_sync(FULL, p, 0);
-        if(p >= last) break;
+        uint32_t p = first, band0 = 0;
+        if(!WAVE) {
+            if(lane == 0) p = first + atomicAdd(counter, 1u);
+            p = __shfl_sync(FULL, p, 0);
+            if(p >= last) break;
+        }
         const PairDesc pd = pairs[p];
-        if(results[pd.orig].status != 0 || pd.la == 0 || pd.lb == 0) continue;
+        if(results[pd.orig].status != 0 || pd.la == 0 || pd.lb == 0) {
+            if(WAVE) break;
+            continue;
+        }
         const uint32_t la = pd.la, lb = pd.lb;
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;
@@ -102,17 +126,35 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         const uint32_t nblocks = pipe_nblocks(lb);
         const uint32_t nbands = (la + H - 1) / H;
         const uint32_t nsteps = lb + 31;
+        if(WAVE) {
+            if(lane == 0) band0 = atomicAdd(counter, 1u);
+            band0 = __shfl_sync(FULL, band0, 0);
+            if(band0 >= nbands) break;
+            bnd = reinterpret_cast<float2*>(bnd_all);  // wave_bnd[band] = bnd + band * 2 * bnd_stride
+        }
 
         // row above band 0 = top margin row r = 0 (align_pair.cc:88-90)
-        for(uint32_t c = 1 + lane; c <= lb; c += 32) {
-            const CellOut o = cell_out<1>(LOWEST, LOWEST, margin_ins<1>(c, g), g);
-            bnd[c] = make_float2(o.X, o.Y);
+        if(!WAVE || band0 == 0) {
+            for(uint32_t c = 1 + lane; c <= lb; c += 32) {
+                const CellOut o = cell_out<1>(LOWEST, LOWEST, margin_ins<1>(c, g), g);
+                bnd[c] = make_float2(o.X, o.Y);
+            }
         }
         __syncwarp();
 
-        for(uint32_t band = 0; band < nbands; ++band) {
-            const float2* bin = bnd + (band & 1) * 2 * bnd_stride;
-            float2* bout = bnd + ((band + 1) & 1) * 2 * bnd_stride;
+        for(uint32_t band = band0; band < (WAVE ? band0 + 1 : nbands); ++band) {
+            const float2* bin = bnd + (size_t)(WAVE ? band : (band & 1)) * 2 * bnd_stride;
+            float2* bout = bnd + (size_t)(WAVE ? band + 1 : ((band + 1) & 1)) * 2 * bnd_stride;
+            // WAVE: one column of the row above per lane, polled until the producer's value is there
+            auto load_block = [&](uint32_t col0) {
+                const float2* src = bin + min(col0 + (uint32_t)lane, lb);
+                float2 v = ld_relaxed_f2(src);
+                while(__any_sync(FULL, v.x != v.x)) {  // NaN sentinel: not written yet
+                    __nanosleep(40);
+                    v = ld_relaxed_f2(src);
+                }
+                return v;
+            };
             const uint32_t r0 = band * H + lane * R + 1;  // first row of this lane
             // ---- private substitution rows: s_tab[h][nuc][lane] = rows 4h..4h+3 ---------------
 #pragma unroll
@@ -144,7 +186,19 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             // lane 31's outgoing registers carry lane 0's inputs: row above the band + symbol
             float outX = 0.f, outY = 0.f;
             uint32_t boff = 0;
-            if(lane == 31) {
+            // WAVE: the row above comes from another SM through L2, far too slow to fetch one column
+            // per step on the critical path; keep two 32-column blocks of it (and of the symbols) in
+            // registers, one column per lane, refilled a whole block ahead of use.
+            float2 blkA = make_float2(0.f, 0.f), blkB = blkA;
+            uint32_t symA = 0, symB = 0;
+            if(WAVE) {
+                const float2 first = load_block(1u - (uint32_t)lane);  // every lane: column 1
+                blkA = load_block(2u);
+                symA = b[min(1u + lane, lb - 1)];
+                blkB = load_block(2u + WAVE_BLOCK);
+                symB = b[min(1u + WAVE_BLOCK + lane, lb - 1)];
+                if(lane == 31) outX = first.x, outY = first.y, boff = (uint32_t)b[0] * 512u;
+            } else if(lane == 31) {
                 const float2 v = bin[1];
                 outX = v.x, outY = v.y;
                 boff = (uint32_t)b[0] * 512u;
@@ -156,10 +210,24 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                 const float recvX = __shfl_sync(FULL, outX, rot);
                 const float recvY = __shfl_sync(FULL, outY, rot);
                 const uint32_t bo = __shfl_sync(FULL, boff, rot);
-                // lane 0's inputs for the NEXT step (column t + 2), uniform addresses
-                const uint32_t cn = min(t + 2, lb);
-                const float2 bnv = bin[cn];
-                const uint32_t bl = b[cn - 1];
+                // lane 0's inputs for the NEXT step (column t + 2)
+                float2 bnv;
+                uint32_t bl;
+                if(WAVE) {
+                    constexpr uint32_t WB = WAVE_BLOCK;
+                    if((t & (WB - 1)) == 0 && t != 0) {  // block t / WB becomes current; refill the next
+                        blkA = blkB, symA = symB;
+                        blkB = load_block(t + WB + 2);
+                        symB = b[min(t + WB + 1 + lane, lb - 1)];
+                    }
+                    bnv.x = __shfl_sync(FULL, blkA.x, t & (WB - 1));
+                    bnv.y = __shfl_sync(FULL, blkA.y, t & (WB - 1));
+                    bl = __shfl_sync(FULL, symA, t & (WB - 1));
+                } else {  // uniform addresses, written by this warp one band earlier
+                    const uint32_t cn = min(t + 2, lb);
+                    bnv = bin[cn];
+                    bl = b[cn - 1];
+                }
                 if(u < lb) {
                     const uint32_t bm = 1u << (31 - (t & 31));
                     float sv[R4 * 4];
@@ -217,6 +285,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             }
             __syncwarp();  // bout of this band is bin of the next
         }
+        if(WAVE) continue;  // next band ticket
     }
 }
 

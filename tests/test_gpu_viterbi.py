@@ -191,3 +191,37 @@ def test_raw_sample_files_are_rejected_like_the_reference():
     (_, anc), (_, des) = util.load_fasta("example-10k")
     with pytest.raises(ValueError, match="Early stop codon"):
         oracle.encode_pair(anc, des)
+
+
+def test_wavefront_kernel_equals_inter_pair_kernel(tables):
+    """Long pairs run as an intra-pair wavefront (bands of one lattice spread over all SMs); the
+    result must be identical to the one-warp-per-pair kernel and to the oracle."""
+    import coati_b200
+    T = tables["mg_golden"]
+    (_, anc), (_, des) = util.load_fasta("benchmark_4k")
+    anc, _ = oracle.trim_end_stop(anc)
+    des, _ = oracle.trim_end_stop(des)
+    a, b = oracle.encode_pair(anc, des)
+    want = oracle.viterbi(anc, des, T, enc=(a, b))
+    outs = []
+    for env in ("0", "1"):
+        os.environ["COATI_GPU_NO_WAVE"] = env
+        try:
+            ctx = coati_b200.Context(0)
+        finally:
+            del os.environ["COATI_GPU_NO_WAVE"]
+        ctx.set_model(T, oracle.DEFAULT_G, oracle.DEFAULT_E, 1)
+        outs.append(ctx.viterbi(a, b, anc, des))
+        # ragged mini-batch: a long pair next to short ones
+        rng = np.random.RandomState(11)
+        ancs, dess, As, Bs = _random_batch(rng, 5, 1, 60)
+        ancs.append(anc), dess.append(des), As.append(a), Bs.append(b)
+        rows_a, rows_b, score, status = ctx.viterbi_batch(PackedPairs(As, Bs, ancs, dess))
+        assert (status == 0).all()
+        assert (rows_a[-1], rows_b[-1]) == want[:2] and util.f32_bits(score[-1]) == util.f32_bits(want[2])
+        for p in range(5):
+            o = oracle.viterbi(ancs[p], dess[p], T, enc=(As[p], Bs[p]))
+            assert (rows_a[p], rows_b[p]) == o[:2] and util.f32_bits(score[p]) == util.f32_bits(o[2])
+        ctx.close()
+    for got in outs:
+        assert got[:2] == want[:2] and util.f32_bits(got[2]) == util.f32_bits(want[2])
