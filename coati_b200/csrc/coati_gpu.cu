@@ -595,8 +595,8 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                         bt->d_results.p);
             cudaEventRecord(ev[1], s);
             traceback_kernel<DiagLayout, false><<<(cnt + 63) / 64, 64, 0, s>>>(
-                bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,
-                bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+                bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p,
+                bt->d_results.p);
         } else {
             const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg);
             if(!pc) return COATI_GPU_E_ARG;
@@ -630,12 +630,10 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
 #define COATI_TB(RR)                                                                                   \
     if(pc->wave)                                                                                       \
         traceback_kernel<PipeLayoutR<RR>, true><<<cnt, 32, 0, s>>>(                                    \
-            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,          \
-            bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);                                            \
+            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);   \
     else                                                                                               \
         traceback_kernel<PipeLayoutR<RR>, false><<<(cnt + 63) / 64, 64, 0, s>>>(                       \
-            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, bt->d_anc.p, bt->d_des.p, ctx->gap,          \
-            bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p);
+            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);
             switch(pc->R) {
             case 2: COATI_TB(2) break;
             case 3: COATI_TB(3) break;
@@ -647,9 +645,9 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
 #undef COATI_TB
         }
         cudaEventRecord(ev[2], s);
-        compact_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last,
-                                                          bt->d_out_a.p, bt->d_out_b.p,
-                                                          bt->d_results.p);
+        expand_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last, bt->d_anc.p,
+                                                         bt->d_des.p, bt->d_out_a.p, bt->d_out_b.p,
+                                                         bt->d_results.p);
         cudaEventRecord(ev[3], s);
         bt->launches += 3;
     }

@@ -1,4 +1,4 @@
-// Traceback over the packed direction stream + left-alignment of the emitted rows.
+// Traceback over the packed direction stream, then expansion of the path into the two rows.
 //
 // Follows traceback<S>, src/lib/align_pair.cc:249-303: start at the terminal cell with
 // max_mdi(M, D, I) of the adjusted terminal scores, then walk MATCH (-1,-1) / DELETION (-k, 0) /
@@ -89,14 +89,13 @@ struct PipeLayout {
 //               writes the rows, and every 8 steps lane j reads ahead the decision words the path
 //               reaches in 64 + 8j steps if it keeps to its diagonal, so the serial walk finds its
 //               words in L1/L2 instead of paying a DRAM round trip per step.
-// Rows are written right-aligned into the pair's output slot [out_off, out_off + la + lb];
-// compact_rows_kernel moves them to the front afterwards.
+// The walk is a serial dependent chain (index -> load -> decode -> move), so it does nothing else:
+// it records one op byte per alignment column (0 = M, 1 = D, 2 = I), right-aligned in the pair's
+// out_b slot; expand_rows_kernel then builds both rows in parallel with coalesced accesses.
 template <class Layout, bool WARP>
 __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
-                                 const uint8_t* __restrict__ dirs, const char* __restrict__ anc_all,
-                                 const char* __restrict__ des_all, GapConsts gap,
-                                 char* __restrict__ out_a, char* __restrict__ out_b,
-                                 PairResult* __restrict__ results) {
+                                 const uint8_t* __restrict__ dirs, GapConsts gap,
+                                 char* __restrict__ out_b, PairResult* __restrict__ results) {
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t p = first + (WARP ? gtid >> 5 : gtid);
     const uint32_t lane = WARP ? (threadIdx.x & 31) : 0;
@@ -106,11 +105,8 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
     PairResult& res = results[pd.orig];
     if(res.status != 0) return;
     const uint32_t la = pd.la, lb = pd.lb, k = gap.k;
-    const char* anc = anc_all + pd.a_off;
-    const char* des = des_all + pd.b_off;
     const uint8_t* dir = dirs + pd.dir_off;
-    char* oa = out_a + pd.out_off;
-    char* ob = out_b + pd.out_off;
+    char* ops = out_b + pd.out_off;
 
     uint32_t r = la, c = lb, pos = la + lb;
     int st;
@@ -140,29 +136,20 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
         if(st == ST_M) {
             if(r == 0 || c == 0) { err = 1; break; }
             --pos;
-            if(lead) {
-                oa[pos] = anc[r - 1];
-                ob[pos] = des[c - 1];
-            }
+            if(lead) ops[pos] = ST_M;
             --r, --c;
         } else if(st == ST_D) {
             if(r < k) { err = 1; break; }
             for(uint32_t q = 0; q < k; ++q) {
                 --pos;
-                if(lead) {
-                    oa[pos] = anc[r - 1 - q];
-                    ob[pos] = '-';
-                }
+                if(lead) ops[pos] = ST_D;
             }
             r -= k;
         } else {
             if(c < k) { err = 1; break; }
             for(uint32_t q = 0; q < k; ++q) {
                 --pos;
-                if(lead) {
-                    oa[pos] = '-';
-                    ob[pos] = des[c - 1 - q];
-                }
+                if(lead) ops[pos] = ST_I;
             }
             c -= k;
         }
@@ -187,35 +174,44 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
     res.start = pos;
 }
 
-// One warp per pair: move the right-aligned rows to the start of the slot and NUL-terminate.
-// Forward chunked copy is safe for overlapping ranges because src >= dst.
-__global__ void compact_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first,
-                                    uint32_t last, char* __restrict__ out_a,
-                                    char* __restrict__ out_b,
-                                    const PairResult* __restrict__ results) {
+// One warp per pair: expand the op bytes (right-aligned in the out_b slot, first op at res.start)
+// into the two gapped rows, left-aligned and NUL-terminated (align_pair.cc:270-302: MATCH emits
+// (anc, des), DELETION (anc, '-'), INSERTION ('-', des); the reference reverses at the end, here the
+// ops are simply read front to back).  Source indices are running counts of the ops seen so far
+// (warp ballot + popcount).  In-place on out_b is safe: chunk i is read before chunk i is written and
+// reads never trail writes (read index = write index + start).
+__global__ void expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+                                   const char* __restrict__ anc_all, const char* __restrict__ des_all,
+                                   char* __restrict__ out_a, char* __restrict__ out_b,
+                                   const PairResult* __restrict__ results) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t p = first + warp;
     if(p >= last) return;
     const PairDesc pd = pairs[p];
     const PairResult res = results[pd.orig];
+    const char* anc = anc_all + pd.a_off;
+    const char* des = des_all + pd.b_off;
     char* oa = out_a + pd.out_off;
     char* ob = out_b + pd.out_off;
     const uint32_t n = res.status == 0 ? res.len : 0, shift = res.start;
-    if(shift != 0) {
-        for(uint32_t base = 0; base < n; base += 32) {
-            const uint32_t x = base + lane;
-            char va = 0, vb = 0;
-            if(x < n) {
-                va = oa[shift + x];
-                vb = ob[shift + x];
-            }
-            __syncwarp();
-            if(x < n) {
-                oa[x] = va;
-                ob[x] = vb;
-            }
-            __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t ia = 0, ib = 0;
+    for(uint32_t base = 0; base < n; base += 32) {
+        const uint32_t x = base + lane;
+        const int op = x < n ? ob[shift + x] : -1;
+        const bool useA = op == ST_M || op == ST_D, useB = op == ST_M || op == ST_I;
+        const uint32_t ma = __ballot_sync(0xffffffffu, useA), mb = __ballot_sync(0xffffffffu, useB);
+        char va = '-', vb = '-';
+        if(useA) va = anc[ia + __popc(ma & lt)];
+        if(useB) vb = des[ib + __popc(mb & lt)];
+        __syncwarp();
+        if(x < n) {
+            oa[x] = va;
+            ob[x] = vb;
         }
+        ia += __popc(ma);
+        ib += __popc(mb);
+        __syncwarp();
     }
     if(lane == 0) {
         oa[n] = 0;
