@@ -256,8 +256,26 @@ def main():
     # ---- device-resident metric -----------------------------------------------------------------
     batch = ctx.batch(w["a_off"], w["b_off"])
     batch.upload(w["a_all"], w["b_all"], w["anc_all"], w["des_all"])
-    for _ in range(args.warmup):
+    gather_bytes = 0
+    if dist is not None:
+        # result gather to rank 0 (the path's only collective): device-resident rows + per-pair records
+        from coati_b200 import dist as cdist
+        bufs = batch.device_buffers()
+        dev = torch.device("cuda", local)
+        payload = {"out_a": cdist.DeviceBytes(bufs["out_a"], bufs["out_bytes"]).tensor(dev),
+                   "out_b": cdist.DeviceBytes(bufs["out_b"], bufs["out_bytes"]).tensor(dev),
+                   "results": cdist.DeviceBytes(bufs["results"], bufs["result_bytes"]).tensor(dev)}
+        recv_cache = {}
+        gather_bytes = 2 * bufs["out_bytes"] + bufs["result_bytes"]
+
+    def run_step():
         batch.run()
+        if dist is not None:
+            with torch.cuda.stream(stream):
+                cdist.gather_to_root(payload, 0, recv_cache)
+
+    for _ in range(args.warmup):
+        run_step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -267,7 +285,7 @@ def main():
     ev0.record(stream)
     fill_ms = trace_ms = compact_ms = 0.0
     for _ in range(args.steps):
-        batch.run()
+        run_step()
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -339,7 +357,8 @@ def main():
         "config": {"workload": wl["desc"], "pairs_per_gpu": npairs, "k": wl["k"], "seed": wl["seed"],
                    "cells_per_gpu": cells, "l2": "inputs + decision stream >> 126 MB L2 (no flush needed)",
                    "decision_stream_bytes_per_gpu": stats["dir_bytes"], "chunks": stats["chunks"],
-                   "gen_seconds": gen_s},
+                   "gen_seconds": gen_s,
+                   "nccl_gather_bytes_per_rank_per_step": gather_bytes},
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "pairs_per_s": pairs_all * e2e_steps / e2e_s,
                 "steps": e2e_steps},
