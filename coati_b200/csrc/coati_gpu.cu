@@ -153,6 +153,7 @@ typedef void (*pipe1_kernel_t)(const PairDesc*, uint32_t, uint32_t, unsigned int
 struct PipeCfg {
     uint32_t k, R;
     bool wave;
+    uint32_t nc;  // substitution columns held per lane (16, or 4 for ACGT-only descendants)
     pipe_kernel_t fn;    // generic-K pipelined kernel (viterbi_pipe.cuh)
     pipe1_kernel_t fn1;  // K = 1 specialisation (viterbi_pipe1.cuh); takes precedence when set
     size_t smem;
@@ -161,22 +162,28 @@ struct PipeCfg {
 };
 template <int K, int R>
 PipeCfg make_cfg() {
-    return PipeCfg{(uint32_t)K, (uint32_t)R, false, viterbi_pipe_kernel<K, R>, nullptr,
+    return PipeCfg{(uint32_t)K, (uint32_t)R, false, 16, viterbi_pipe_kernel<K, R>, nullptr,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
 }
-template <int R, bool WAVE>
+template <int R, bool WAVE, int NC>
 PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false) or intra-pair wavefront
-    return PipeCfg{1u, (uint32_t)R, WAVE, nullptr, viterbi_pipe1_kernel<R, WAVE>,
-                   (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
+    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, nullptr, viterbi_pipe1_kernel<R, WAVE, NC>,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
 }
-PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false>(), make_cfg1<8, false>(), make_cfg<3, 3>(),
-                         make_cfg<3, 6>(),      make_cfg1<2, true>(),  make_cfg1<4, true>(),
-                         make_cfg1<8, true>()};
+PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false, 16>(), make_cfg1<8, false, 16>(), make_cfg<3, 3>(),
+                         make_cfg<3, 6>(),          make_cfg1<2, true, 16>(),  make_cfg1<4, true, 16>(),
+                         make_cfg1<8, true, 16>(),  make_cfg1<4, false, 4>(),  make_cfg1<8, false, 4>(),
+                         make_cfg1<8, true, 4>()};
 
-const PipeCfg* find_cfg(uint32_t k, uint32_t cfg) {
+// nc = 4 picks the ACGT-only variant when it exists, else falls back to the 16-column kernel
+const PipeCfg* find_cfg(uint32_t k, uint32_t cfg, uint32_t nc = 16) {
+    const PipeCfg* fallback = nullptr;
     for(const PipeCfg& pc : g_pipe_cfgs)
-        if(pc.k == k && pc.R == (cfg & 0xffu) && pc.wave == ((cfg & CFG_WAVE) != 0)) return &pc;
-    return nullptr;
+        if(pc.k == k && pc.R == (cfg & 0xffu) && pc.wave == ((cfg & CFG_WAVE) != 0)) {
+            if(pc.nc == nc) return &pc;
+            if(pc.nc == 16) fallback = &pc;
+        }
+    return fallback;
 }
 
 // issue-slot model of one pair on one warp: bands x steps x (R cells + per-step overhead)
@@ -205,6 +212,7 @@ struct coati_gpu_batch {
     DevBuf<float4> d_bnd;
     DevBuf<uint32_t> d_prog;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
+    uint32_t nc = 16;  // 4 when every descendant symbol of the batch is A/C/G/T (set at upload)
     std::vector<PairResult> h_results;
     std::vector<cudaEvent_t> events;  // 4 per run: fill start, fill end, traceback end, compact end
     ~coati_gpu_batch() {
@@ -486,7 +494,9 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
             wave_f4 = std::max<uint64_t>(wave_f4, (uint64_t)(nb + 1) * ((d.lb + 4) / 2));
         } else {
             const uint32_t want = (r.last - r.first + PIPE_WARPS - 1) / PIPE_WARPS;
-            const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
+            const PipeCfg* pc4 = find_cfg(k, r.cfg, 4);  // ACGT-only variant may be more resident
+            const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount *
+                                 std::max(pc->ctas_per_sm, pc4 ? pc4->ctas_per_sm : 0);
             bt->bnd_ctas = std::max(bt->bnd_ctas, std::min(want, cap));
         }
     }
@@ -546,6 +556,16 @@ extern "C" int coati_gpu_batch_upload(coati_gpu_batch* bt, const uint8_t* a_all,
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_anc.p, anc_all, bt->a_total, cudaMemcpyHostToDevice, s));
     }
     if(bt->b_total) {
+        // ambiguity codes anywhere in the batch?  (decides the shared-memory footprint of the fill)
+        uint64_t acc8 = 0;
+        const uint64_t n8 = bt->b_total / 8;
+        const uint64_t* w8 = reinterpret_cast<const uint64_t*>(b_all);
+        if((reinterpret_cast<uintptr_t>(b_all) & 7) == 0)
+            for(uint64_t x = 0; x < n8; ++x) acc8 |= w8[x];
+        else
+            acc8 = ~0ull;
+        for(uint64_t x = n8 * 8; x < bt->b_total; ++x) acc8 |= b_all[x];
+        bt->nc = (acc8 & 0xfcfcfcfcfcfcfcfcull) ? 16 : 4;
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_b.p, b_all, bt->b_total, cudaMemcpyHostToDevice, s));
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_des.p, des_all, bt->b_total, cudaMemcpyHostToDevice, s));
     }
@@ -598,7 +618,7 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                 bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p,
                 bt->d_results.p);
         } else {
-            const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg);
+            const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg, bt->nc);
             if(!pc) return COATI_GPU_E_ARG;
             const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
             if(pc->wave) {

@@ -85,7 +85,10 @@ __device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
 }
 constexpr uint32_t WAVE_BLOCK = 32;  // columns of the row above fetched per refill (one per lane)
 
-template <int R, bool WAVE>
+// NC = substitution-table columns kept per lane: 16 (all IUPAC codes) or 4 when no descendant of the
+// batch carries an ambiguity code (the common case) -- a quarter of the shared memory, so more
+// resident warps to fill issue slots.
+template <int R, bool WAVE, int NC>
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
@@ -98,7 +101,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     constexpr uint32_t WPL = (5 * R + 3) & ~3u;
     extern __shared__ float4 s_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4* s_tab = s_dyn + (size_t)warp * R4 * 16 * 32;
+    float4* s_tab = s_dyn + (size_t)warp * R4 * NC * 32;
     float2* bnd = reinterpret_cast<float2*>(bnd_all + ((size_t)blockIdx.x * PIPE_WARPS + warp) * 2 * bnd_stride);
     (void)prog;
     const uint32_t FULL = 0xffffffffu;
@@ -159,18 +162,18 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             // ---- private substitution rows: s_tab[h][nuc][lane] = rows 4h..4h+3 ---------------
 #pragma unroll
             for(int h = 0; h < R4; ++h) {
-                float rowv[4][16];
+                float rowv[4][NC];
 #pragma unroll
                 for(int x = 0; x < 4; ++x) {
                     const uint32_t r = r0 + 4 * h + x;
                     const bool ok = (4 * h + x < R) && r <= la;
                     const uint32_t code = ok ? a[r - 1] : 0;
 #pragma unroll
-                    for(int n = 0; n < 16; ++n) rowv[x][n] = ok ? table[code * TABLE_LD + n] : 0.0f;
+                    for(int n = 0; n < NC; ++n) rowv[x][n] = ok ? table[code * TABLE_LD + n] : 0.0f;
                 }
 #pragma unroll
-                for(int n = 0; n < 16; ++n)
-                    s_tab[(h * 16 + n) * 32 + lane] = make_float4(rowv[0][n], rowv[1][n], rowv[2][n], rowv[3][n]);
+                for(int n = 0; n < NC; ++n)
+                    s_tab[(h * NC + n) * 32 + lane] = make_float4(rowv[0][n], rowv[1][n], rowv[2][n], rowv[3][n]);
             }
             // ---- state at column 0 (left margin, align_pair.cc:84-87) -------------------------
             float Xp[R], Zp[R], diagX;
@@ -233,7 +236,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     float sv[R4 * 4];
 #pragma unroll
                     for(int h = 0; h < R4; ++h) {
-                        const float4 v = *reinterpret_cast<const float4*>(tab_lane + bo + h * 8192);
+                        const float4 v = *reinterpret_cast<const float4*>(tab_lane + bo + h * (NC * 512));
                         sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
                     }
                     float D = recvY, dXq = diagX;
