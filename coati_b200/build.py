@@ -8,6 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcoati_gpu.so")
+CLI = os.path.join(HERE, "bin", "coati-gpu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 # -fmad=false: the Viterbi parity contract is an op-order contract; FADD/FADD must
@@ -38,13 +39,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cus = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
     ccs = sorted(os.path.join(CSRC, "host", f) for f in os.listdir(os.path.join(CSRC, "host"))
-                 if f.endswith(".cc")) if os.path.isdir(os.path.join(CSRC, "host")) else []
+                 if f.endswith(".cc") and f != "cli_main.cc") if os.path.isdir(os.path.join(CSRC, "host")) else []
     cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + cus + ccs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libcoati_gpu.so")
+    # the CLI front end (coati-gpu alignpair|sample), linked against the library next to it
+    os.makedirs(os.path.join(HERE, "bin"), exist_ok=True)
+    cli = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-o", CLI,
+           os.path.join(CSRC, "host", "cli_main.cc"), "-L" + HERE, "-lcoati_gpu", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cli, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building coati-gpu")
     return LIB
 
 

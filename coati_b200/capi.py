@@ -71,6 +71,16 @@ def load_library() -> C.CDLL:
     lib.coati_synth_fill.restype = None
     lib.coati_gpu_batch_destroy.argtypes = [vp]
     lib.coati_gpu_batch_destroy.restype = None
+    # host layer (no GPU): table builder, encoding, seeding, re-scoring
+    lib.coati_host_marginal_table.argtypes = [C.c_int, C.c_float, C.c_float, _fp, C.c_int, C.c_int, _fp]
+    lib.coati_host_mg94_p.argtypes = [C.c_float, C.c_float, _fp, _fp, _fp]
+    lib.coati_host_gtr_q.argtypes = [_fp, _fp, _fp]
+    lib.coati_host_encode.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, _u8p, _u8p]
+    lib.coati_host_seed.argtypes = [C.POINTER(C.c_char_p), C.c_size_t, _u64p]
+    lib.coati_host_seed.restype = None
+    lib.coati_host_alignment_score.argtypes = [C.c_char_p, C.c_char_p, _fp, C.c_float, C.c_float, C.c_size_t, _fp]
+    lib.coati_host_json_number.argtypes = [C.c_float, C.c_char_p, C.c_size_t]
+    lib.coati_host_json_number.restype = None
     lib.coati_gpu_forward.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(vp)]
     lib.coati_gpu_forward_terminal.argtypes = [vp, _fp, _fp]
     lib.coati_gpu_sampleback.argtypes = [vp, C.c_char_p, C.c_char_p, _u64p, C.c_size_t, vp, vp,
@@ -340,3 +350,27 @@ def synth_pairs(n: int, workload: int = 5, seed: int = 42, first: int = 0, sub: 
                          b_off.ctypes.data_as(_u64p), _vp(out["anc_all"]), _vp(out["des_all"]),
                          _vp(out["a_all"]), _vp(out["b_all"]))
     return out
+
+
+# ---- host layer helpers (C++ table builder / sequence prep behind coati_host_* entry points) ---------
+def host_marginal_table(model="mar-mg", br_len=0.0133, omega=0.2, pi=(0.308, 0.185, 0.199, 0.308),
+                        amb="SUM", msub="SUM"):
+    lib = load_library()
+    out = np.zeros((183, 15), dtype=np.float32)
+    p = np.asarray(pi, dtype=np.float32)
+    rc = lib.coati_host_marginal_table({"mar-mg": 0, "mar-ecm": 1}[model], br_len, omega, p.ctypes.data_as(_fp),
+                                       int(amb == "BEST"), int(msub == "MAX"), out.ctypes.data_as(_fp))
+    if rc != 0:
+        raise ValueError("set_subst failed")
+    return out
+
+
+def host_encode(anc: str, des: str):
+    lib = load_library()
+    ab, db = anc.encode("latin-1"), des.encode("latin-1")
+    a = np.zeros(len(ab), dtype=np.uint8)
+    b = np.zeros(len(db), dtype=np.uint8)
+    rc = lib.coati_host_encode(ab, len(ab), db, len(db), a.ctypes.data_as(_u8p), b.ctypes.data_as(_u8p))
+    if rc != 0:
+        raise CoatiGpuError(rc, lib.coati_gpu_strerror(rc).decode())
+    return a, b

@@ -1,0 +1,128 @@
+"""CPU: the C++ host layer above the C ABI (coati_b200/csrc/host) -- table builder, sequence prep,
+seeding, re-scoring, output formatting -- against the oracle's independent numpy/C restatements and the
+reference's known answers."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from coati_b200 import capi
+from coati_b200 import build as cbuild
+from oracle import table as otable
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_fp = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    cbuild.build()
+    return capi.load_library()
+
+
+def test_mg94_p_vs_reference_golden(lib):
+    """mutation_coati.cc:129-145: P against the reference's golden mg94P at its own tolerance."""
+    P = np.zeros((61, 61), np.float32)
+    pi = np.float32([0.308, 0.185, 0.199, 0.308])
+    assert lib.coati_host_mg94_p(0.0133, 0.2, pi.ctypes.data_as(_fp), None, P.ctypes.data_as(_fp)) == 0
+    np.testing.assert_allclose(P, np.load(util.GOLDEN + "/mg94_p_default.npy"), rtol=1e-5, atol=1e-9)
+    assert lib.coati_host_mg94_p(0.0, 0.2, pi.ctypes.data_as(_fp), None, P.ctypes.data_as(_fp)) != 0  # br_len <= 0
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(model="mar-ecm"), dict(br_len=0.05, omega=0.5, pi=(0.25,) * 4),
+                                dict(amb="BEST"), dict(msub="MAX"), dict(model="mar-ecm", br_len=0.4),
+                                dict(br_len=2.5, omega=1.3)])
+def test_marginal_table_vs_oracle_builder(kw, lib):
+    """C++ float Pade expm + marginalisation vs the oracle's float64 scipy expm (table parity is pinned to
+    the reference's 1e-5 tolerance only)."""
+    got = capi.host_marginal_table(**kw)
+    want = otable.build_table(**kw)
+    np.testing.assert_allclose(got, want, rtol=3e-5, atol=3e-6)
+
+
+def test_marginal_p_normalised(lib):
+    """mutation_coati.cc:206-222."""
+    T = capi.host_marginal_table()
+    s = (np.exp(T[:, :4].astype(np.float64)) * np.array(otable.DEFAULT_PI)).sum(axis=1)
+    np.testing.assert_allclose(s, 1.0, rtol=2e-5)
+
+
+def test_gtr_q_golden(lib):
+    """mutation_coati.cc:358-386."""
+    pi = np.float32([0.308, 0.185, 0.199, 0.308])
+    sg = np.float32([0.009489730, 0.039164824, 0.004318182, 0.015438693, 0.038734091, 0.008550000])
+    q = np.zeros(16, np.float32)
+    assert lib.coati_host_gtr_q(pi.ctypes.data_as(_fp), sg.ctypes.data_as(_fp), q.ctypes.data_as(_fp)) == 0
+    exp = [[-0.010879400, 0.001755600, 0.007793800, 0.00133], [0.002922837, -0.017925237, 0.003072300, 0.0119301],
+           [0.012062766, 0.002856158, -0.017552324, 0.0026334], [0.001330000, 0.007165807, 0.001701450, -0.010197257]]
+    np.testing.assert_allclose(q.reshape(4, 4), exp, rtol=2e-5, atol=1e-8)
+    sg[0] = -0.1
+    assert lib.coati_host_gtr_q(pi.ctypes.data_as(_fp), sg.ctypes.data_as(_fp), q.ctypes.data_as(_fp)) != 0
+
+
+def test_encoding_matches_oracle_and_reference_goldens(lib):
+    """utils.cc:532-586."""
+    a, b = capi.host_encode("AAAGGGTTTCCCACTAGA", "ACGTRYMKSWBDHVN-")
+    assert list(a) == [0, 1, 2, 126, 127, 128, 180, 181, 182, 63, 64, 65, 21, 22, 23, 24, 25, 26]
+    assert list(b) == list(range(16))
+    rng = np.random.RandomState(4)
+    for _ in range(30):
+        anc, des = util.random_pair(rng, int(rng.randint(1, 40)), ambiguous=True)
+        oa, ob = oracle.encode_pair(anc, des)
+        ha, hb = capi.host_encode(anc, des)
+        assert np.array_equal(oa, ha) and np.array_equal(ob, hb)
+    with pytest.raises(capi.CoatiGpuError) as e:
+        capi.host_encode("AAATAA", "A")
+    assert e.value.code == -7 and "Early stop codon" in str(e.value)
+    with pytest.raises(capi.CoatiGpuError) as e:
+        capi.host_encode("AANAAA", "A")
+    assert e.value.code == -6 and "Ambiguous" in str(e.value)
+
+
+def test_seeding_matches_oracle(lib):
+    for seeds in (["42"], [""], ["random42"], ["-5", "x"], ["2147483648"], ["1", "2", "3", "4", "5", "6", "7", "8", "9"]):
+        st = (C.c_uint64 * 2)()
+        arr = (C.c_char_p * len(seeds))(*[s.encode() for s in seeds])
+        lib.coati_host_seed(arr, len(seeds), st)
+        o = oracle.seed_state(seeds)
+        assert [st[0], st[1]] == [int(o[0]), int(o[1])], seeds
+
+
+def test_alignment_score_goldens(lib, tables):
+    """align_marginal.cc:490-509 through the C++ host implementation."""
+    from tests.test_oracle_golden import SCORES
+    T = tables["mg_golden"]
+    for a, b, exp in SCORES:
+        sc = C.c_float(0)
+        rc = lib.coati_host_alignment_score(a.encode(), b.encode(), T.ctypes.data_as(_fp), oracle.DEFAULT_G,
+                                            oracle.DEFAULT_E, 1, C.byref(sc))
+        assert rc == 0
+        assert sc.value == pytest.approx(exp, rel=1e-5, abs=1e-5)
+        assert util.f32_bits(sc.value) == util.f32_bits(oracle.alignment_score(a, b, T))
+    sc = C.c_float(0)
+    assert lib.coati_host_alignment_score(b"CTCTGGATAGTG", b"CTATAGTG", T.ctypes.data_as(_fp), oracle.DEFAULT_G,
+                                          oracle.DEFAULT_E, 1, C.byref(sc)) != 0
+
+
+def test_json_number_is_shortest_roundtrip_double(lib):
+    """json.cc: nlohmann dumps the float score widened to double (align_marginal.cc:655-670 literals)."""
+    buf = C.create_string_buffer(64)
+    for v, s in ((np.float32(-1.9466571807861328), "-1.9466571807861328"), (0.0, "0.0"), (0.1, "0.10000000149011612"),
+                 (np.float32(-1.6172490119934082), "-1.6172490119934082"), (3.0, "3.0")):
+        lib.coati_host_json_number(C.c_float(float(v)), buf, 64)
+        assert buf.value.decode() == s
+
+
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    fa = tmp_path / "x.fasta"
+    fa.write_text(">1\nCTCTGGATAGTG\n>2\nCTATAGTG\n")
+    r = subprocess.run([os.path.join(ROOT, "coati_b200", "bin", "coati-gpu"), "alignpair", str(fa)],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
