@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "forward.cuh"
+#include "sample_spec.cuh"
 #include "traceback.cuh"
 #include "viterbi_generic.cuh"
 #include "viterbi_pipe.cuh"
@@ -850,6 +851,11 @@ struct coati_gpu_forward_t {
     DevBuf<uint64_t> d_rng, d_out_off;
     DevBuf<uint32_t> d_len, d_start;
     DevBuf<int32_t> d_status;
+    DevBuf<SampleRec> d_rec;   // per (cell, state) sampling records (sample_spec.cuh), built lazily
+    DevBuf<U128> d_pw;         // MULT^(2^i)
+    DevBuf<uint32_t> d_draws;
+    DevBuf<uint64_t> d_starts, d_cursor;
+    bool rec_ready = false;
     float term[3] = {0, 0, 0};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float fill_ms = 0, sample_ms = 0;
@@ -897,7 +903,7 @@ extern "C" int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La
     if(La) CU_TRY(ctx, cudaMemcpyAsync(h->d_a.p, a, La, cudaMemcpyHostToDevice, s));
     if(Lb) CU_TRY(ctx, cudaMemcpyAsync(h->d_b.p, b, Lb, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaEventRecord(h->ev[0], s));
-    forward_fill_kernel<<<1, 256, 0, s>>>(h->d_desc.p, 1, h->d_a.p, h->d_b.p, ctx->d_table, ctx->gap,
+    forward_fill_kernel<<<1, 1023, 0, s>>>(h->d_desc.p, 1, h->d_a.p, h->d_b.p, ctx->d_table, ctx->gap,
                                           h->d_mats.p, h->d_term.p);
     ++ctx->launches;
     CU_TRY(ctx, cudaEventRecord(h->ev[1], s));
@@ -960,6 +966,84 @@ extern "C" int coati_gpu_sampleback(coati_gpu_forward_t* h, const char* anc, con
     }
     const uint64_t zero = 0;
     const uint64_t st[2] = {rng_state[0] | 1ull, rng_state[1]};  // Lehmer64Fast::SetState (random.hpp:131-134)
+    static const bool serial_env = [] {
+        const char* e = std::getenv("COATI_GPU_SAMPLE_SERIAL");
+        return e && e[0] == '1';
+    }();
+    if(n >= 4 && !serial_env) {
+        // ---- parallel path: records -> speculative draw counts -> chase -> parallel re-walk ----------
+        const uint64_t ncells = (uint64_t)(h->la + 1) * (h->lb + 1);
+        const uint64_t max_draws = (uint64_t)h->la + h->lb + 1;
+        const uint32_t window = (uint32_t)std::min<uint64_t>(n * max_draws, 1ull << 19);
+        U128 pw[64];
+        pw[0] = U128{0xda942042e4dd58b5ull, 0};
+        for(int i = 1; i < 64; ++i) pw[i] = mul128(pw[i - 1], pw[i - 1]);
+        cudaError_t e2 = cudaSuccess;
+        auto ok2 = [&](cudaError_t r) {
+            if(e2 == cudaSuccess) e2 = r;
+        };
+        if(!h->rec_ready) ok2(h->d_rec.alloc(3 * ncells + 1, &ctx->pool));
+        ok2(h->d_pw.alloc(64, &ctx->pool));
+        ok2(h->d_draws.alloc(window, &ctx->pool));
+        ok2(h->d_starts.alloc(n, &ctx->pool));
+        ok2(h->d_cursor.alloc(4, &ctx->pool));
+        if(e2 != cudaSuccess) {
+            ctx->last_error = std::string("sampleback allocation: ") + cudaGetErrorString(e2);
+            cudaGetLastError();
+            return COATI_GPU_E_NOMEM;
+        }
+        if(h->la) CU_TRY(ctx, cudaMemcpyAsync(h->d_anc.p, anc, h->la, cudaMemcpyHostToDevice, s));
+        if(h->lb) CU_TRY(ctx, cudaMemcpyAsync(h->d_des.p, des, h->lb, cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemcpyAsync(h->d_pw.p, pw, sizeof(pw), cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemsetAsync(h->d_cursor.p, 0, 4 * sizeof(uint64_t), s));
+        CU_TRY(ctx, cudaEventRecord(h->ev[1], s));
+        const FwdDesc fd{0, 0, 0, h->la, h->lb};
+        if(!h->rec_ready) {
+            sample_records_kernel<<<(unsigned)((ncells + 127) / 128), 128, 0, s>>>(
+                fd, h->d_mats.p, h->d_term.p, ctx->d_table, h->d_a.p, h->d_b.p, ctx->gap, h->d_rec.p);
+            ++ctx->launches;
+            h->rec_ready = true;
+        }
+        const U128 state0{st[0], st[1]};
+        uint64_t cursor[3] = {0, 0, 0};
+        while(cursor[1] < n) {
+            const uint64_t base = cursor[0];
+            spec_steps_kernel<<<(window + 127) / 128, 128, 0, s>>>(h->d_rec.p, h->la, h->lb, ctx->gap.k, state0,
+                                                                     h->d_pw.p, base, window, h->d_draws.p);
+            chase_kernel<<<1, 1, 0, s>>>(h->d_draws.p, base, window, n, h->d_cursor.p, h->d_starts.p);
+            ctx->launches += 2;
+            CU_TRY(ctx, cudaMemcpyAsync(cursor, h->d_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaStreamSynchronize(s));
+            if(cursor[2] != 0) return COATI_GPU_E_INTERNAL;
+            if(cursor[0] == base && cursor[1] < n) return COATI_GPU_E_INTERNAL;  // no progress
+        }
+        sample_paths_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(h->d_rec.p, h->la, h->lb, ctx->gap.k, state0,
+                                                                      h->d_pw.p, h->d_starts.p, (uint32_t)n,
+                                                                      h->d_out_b.p, h->d_len.p, h->d_start.p,
+                                                                      h->d_scores.p);
+        expand_samples_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(h->la, h->lb, (uint32_t)n, h->d_anc.p,
+                                                                      h->d_des.p, h->d_out_a.p, h->d_out_b.p,
+                                                                      h->d_len.p, h->d_start.p);
+        ctx->launches += 2;
+        CU_TRY(ctx, cudaEventRecord(h->ev[2], s));
+        std::vector<uint32_t> lens2(n);
+        CU_TRY(ctx, cudaMemcpyAsync(out_a, h->d_out_a.p, n * stride, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(out_b, h->d_out_b.p, n * stride, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(lens2.data(), h->d_len.p, n * 4, cudaMemcpyDeviceToHost, s));
+        if(scores) CU_TRY(ctx, cudaMemcpyAsync(scores, h->d_scores.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+        CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaEventElapsedTime(&h->sample_ms, h->ev[1], h->ev[2]));
+        if(sample_ms) *sample_ms = h->sample_ms;
+        for(size_t x = 0; x < n; ++x) {
+            if(lens2[x] == 0 && (h->la || h->lb)) return COATI_GPU_E_INTERNAL;
+            if(out_len) out_len[x] = lens2[x];
+        }
+        const U128 fin = jump(state0, cursor[0], pw);  // the stream after all draws of the n samples
+        rng_state[0] = fin.lo;
+        rng_state[1] = fin.hi;
+        return COATI_GPU_OK;
+    }
     if(h->la) CU_TRY(ctx, cudaMemcpyAsync(h->d_anc.p, anc, h->la, cudaMemcpyHostToDevice, s));
     if(h->lb) CU_TRY(ctx, cudaMemcpyAsync(h->d_des.p, des, h->lb, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemcpyAsync(h->d_rng.p, st, sizeof(st), cudaMemcpyHostToDevice, s));

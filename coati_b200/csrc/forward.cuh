@@ -32,7 +32,7 @@ __device__ __forceinline__ float lse3(float x, float y, float z) {  // semiring.
 
 // term: adjusted terminal M, D, I per pair (align_pair.cc:130-138); the matrices keep the
 // un-adjusted values at (La, Lb).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1023)
 forward_fill_kernel(const FwdDesc* __restrict__ pairs, uint32_t npairs,
                     const uint8_t* __restrict__ a_all, const uint8_t* __restrict__ b_all,
                     const float* __restrict__ table, GapConsts g, float* __restrict__ mats,
@@ -49,47 +49,48 @@ forward_fill_kernel(const FwdDesc* __restrict__ pairs, uint32_t npairs,
         float* I = D + plane;
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;
+        // three threads per cell: the M, D and I updates are independent log_sum_exp chains
+        const uint32_t sub = threadIdx.x % 3, slot = threadIdx.x / 3, nslots = blockDim.x / 3;
         for(uint32_t d = 0; d <= la + lb; ++d) {
             const uint32_t rlo = d > lb ? d - lb : 0, rhi = d < la ? d : la;
-            for(uint32_t r = rlo + threadIdx.x; r <= rhi; r += blockDim.x) {
+            for(uint32_t r = rlo + slot; r <= rhi && slot < nslots; r += nslots) {
                 const uint32_t c = d - r;
-                float m, dd, ii;
+                const uint64_t at = (uint64_t)r * ld + c;
+                float v = LOWEST;
                 if(r == 0 || c == 0) {  // align_pair.cc:82-90
-                    m = dd = ii = LOWEST;
-                    if(r == 0 && c == 0) m = 0.0f;
-                    else if(c == 0) { if(r % k == 0) dd = (g.ng + g.go) + g.ge * (float)(r + k - 2); }
-                    else { if(c % k == 0) ii = g.go + g.ge * (float)(c + k - 2); }
-                } else {
+                    if(sub == ST_M) { if(r == 0 && c == 0) v = 0.0f; }
+                    else if(sub == ST_D) { if(c == 0 && r > 0 && r % k == 0) v = (g.ng + g.go) + g.ge * (float)(r + k - 2); }
+                    else { if(r == 0 && c > 0 && c % k == 0) v = g.go + g.ge * (float)(c + k - 2); }
+                } else if(sub == ST_M) {
                     const float s = s_table[a[r - 1] * TABLE_LD + b[c - 1]];
                     const uint64_t dg = (uint64_t)(r - 1) * ld + (c - 1);
                     const float m2m = ((M[dg] + g.ng) + g.ng) + s;
                     const float d2m = (D[dg] + g.gs) + s;
                     const float i2m = ((I[dg] + g.gs) + g.ng) + s;
-                    float uM = LOWEST, uD = LOWEST, uI = LOWEST, lM = LOWEST, lI = LOWEST;
+                    v = lse3(m2m, d2m, i2m);  // :119 plus(mch2mch, del2mch, ins2mch)
+                } else if(sub == ST_D) {
+                    float uM = LOWEST, uD = LOWEST, uI = LOWEST;
                     if(r >= k) {
                         const uint64_t up = (uint64_t)(r - k) * ld + c;
                         uM = M[up], uD = D[up], uI = I[up];
                     }
+                    const float m2d = ((uM + g.ng) + g.go) + g.gk1;
+                    const float i2d = ((uI + g.gs) + g.go) + g.gk1;
+                    const float d2d = uD + g.gk;
+                    v = lse3(m2d, d2d, i2d);  // :120 plus(mch2del, del2del, ins2del)
+                } else {
+                    float lM = LOWEST, lI = LOWEST;
                     if(c >= k) {
                         const uint64_t lf = (uint64_t)r * ld + (c - k);
                         lM = M[lf], lI = I[lf];
                     }
-                    const float m2d = ((uM + g.ng) + g.go) + g.gk1;
-                    const float i2d = ((uI + g.gs) + g.go) + g.gk1;
-                    const float d2d = uD + g.gk;
                     const float m2i = (lM + g.go) + g.gk1;
                     const float i2i = lI + g.gk;
-                    m = lse3(m2m, d2m, i2m);     // :119 plus(mch2mch, del2mch, ins2mch)
-                    dd = lse3(m2d, d2d, i2d);    // :120 plus(mch2del, del2del, ins2del)
-                    ii = log_sum_exp(m2i, i2i);  // :121
+                    v = log_sum_exp(m2i, i2i);  // :121
                 }
-                const uint64_t at = (uint64_t)r * ld + c;
-                M[at] = m, D[at] = dd, I[at] = ii;
-                if(r == la && c == lb) {  // :130-138
-                    term[3 * p + 0] = (m + g.ng) + g.ng;
-                    term[3 * p + 1] = dd + g.gs;
-                    term[3 * p + 2] = (ii + g.gs) + g.ng;
-                }
+                (sub == ST_M ? M : sub == ST_D ? D : I)[at] = v;
+                if(r == la && c == lb)  // :130-138
+                    term[3 * p + sub] = sub == ST_M ? (v + g.ng) + g.ng : sub == ST_D ? v + g.gs : (v + g.gs) + g.ng;
             }
             __threadfence_block();
             __syncthreads();
