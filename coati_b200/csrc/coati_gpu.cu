@@ -78,9 +78,46 @@ struct DevPool {
     }
 };
 
+// same idea for pinned host staging (a D2H copy into pageable memory blocks the host until the whole
+// stream has drained, which would serialise the sub-batch pipeline)
+struct HostPool {
+    struct Block {
+        void* p;
+        size_t bytes;
+        bool used;
+    };
+    std::vector<Block> blocks;
+    void* take(size_t bytes) {
+        if(bytes == 0) return nullptr;
+        Block* best = nullptr;
+        for(Block& b : blocks)
+            if(!b.used && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+        if(best) {
+            best->used = true;
+            return best->p;
+        }
+        void* p = nullptr;
+        if(cudaMallocHost(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        blocks.push_back(Block{p, bytes, true});
+        return p;
+    }
+    void give(void* p) {
+        for(Block& b : blocks)
+            if(b.p == p) b.used = false;
+    }
+    void clear() {
+        for(Block& b : blocks) cudaFreeHost(b.p);
+        blocks.clear();
+    }
+};
+
 struct coati_gpu_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // all work of the public staged API
+    cudaStream_t stream2 = nullptr;  // second lane of the pipelined coati_gpu_viterbi_batch
     cudaDeviceProp prop{};
     bool model_set = false;
     GapConsts gap{};
@@ -91,6 +128,7 @@ struct coati_gpu_ctx {
     bool force_generic = false, no_wave = false;
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
     DevPool pool;
+    HostPool hpool;
 };
 
 #define CU_TRY(ctx, expr)                                                                   \
@@ -197,6 +235,7 @@ double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
 
 struct coati_gpu_batch {
     coati_gpu_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;  // every operation of this batch is ordered on this stream
     size_t npairs = 0;
     uint64_t a_total = 0, b_total = 0, out_total = 0;
     std::vector<PairDesc> descs;  // sorted (largest lattice first)
@@ -214,10 +253,14 @@ struct coati_gpu_batch {
     DevBuf<uint32_t> d_prog;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
     uint32_t nc = 16;  // 4 when every descendant symbol of the batch is A/C/G/T (set at upload)
-    std::vector<PairResult> h_results;
+    PairResult* h_results = nullptr;    // D2H landing zone (pinned, from ctx->hpool)
+    std::vector<PairResult> h_init;     // records of the pairs rejected by host-side validation
+    std::vector<uint32_t> rejected;     // their indices (caller order)
+    bool rejected_known = false;
     std::vector<cudaEvent_t> events;  // 4 per run: fill start, fill end, traceback end, compact end
     ~coati_gpu_batch() {
         for(cudaEvent_t e : events) cudaEventDestroy(e);
+        if(h_results) ctx->hpool.give(h_results);
     }
 };
 
@@ -252,6 +295,7 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     if(cudaSetDevice(device) != cudaSuccess ||
        cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
        cudaMalloc(reinterpret_cast<void**>(&ctx->d_table),
                   TABLE_ROWS * TABLE_LD * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
@@ -295,8 +339,13 @@ extern "C" void coati_gpu_shutdown(coati_gpu_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    if(ctx->stream2) {
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamDestroy(ctx->stream2);
+    }
     if(ctx->d_table) cudaFree(ctx->d_table);
     ctx->pool.trim();
+    ctx->hpool.clear();
     delete ctx;
 }
 
@@ -364,8 +413,19 @@ __global__ void validate_symbols_kernel(const PairDesc* __restrict__ pairs, uint
         results[pd.orig].status = COATI_GPU_E_SYMBOL;
 }
 
+static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
+                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out);
+
 extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const uint64_t* a_off,
                                       const uint64_t* b_off, coati_gpu_batch** out) {
+    if(!ctx) return COATI_GPU_E_ARG;
+    return batch_create_on(ctx, ctx->stream, 1.0, npairs, a_off, b_off, out);
+}
+
+// offsets may start anywhere (a sub-range of a larger CSR pack): everything is stored relative to
+// a_off[0] / b_off[0]
+static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
+                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out) {
     if(!ctx || !out || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
     if(!ctx->model_set || npairs > 0xfffffff0ull) return COATI_GPU_E_ARG;
     *out = nullptr;
@@ -374,25 +434,28 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     coati_gpu_batch* bt = holder.get();
     if(!bt) return COATI_GPU_E_NOMEM;
     bt->ctx = ctx;
+    bt->stream = stream;
     bt->npairs = npairs;
     const uint32_t k = ctx->gap.k;
+    const uint64_t a0 = npairs ? a_off[0] : 0, b0 = npairs ? b_off[0] : 0;
     try {
         bt->descs.resize(npairs);
         bt->host_status.assign(npairs, COATI_GPU_OK);
-        bt->h_results.resize(npairs);
+        bt->h_results = static_cast<PairResult*>(ctx->hpool.take((npairs + 1) * sizeof(PairResult)));
+        if(!bt->h_results) return COATI_GPU_E_NOMEM;
     } catch(const std::bad_alloc&) {
         return COATI_GPU_E_NOMEM;
     }
-    bt->a_total = npairs ? a_off[npairs] : 0;
-    bt->b_total = npairs ? b_off[npairs] : 0;
+    bt->a_total = npairs ? a_off[npairs] - a0 : 0;
+    bt->b_total = npairs ? b_off[npairs] - b0 : 0;
     bt->out_total = bt->a_total + bt->b_total + npairs;
     for(size_t p = 0; p < npairs; ++p) {
         PairDesc& d = bt->descs[p];
         const uint64_t la = a_off[p + 1] - a_off[p], lb = b_off[p + 1] - b_off[p];
         if(la > 0x7fffffffull || lb > 0x7fffffffull) return COATI_GPU_E_ARG;
-        d.a_off = a_off[p];
-        d.b_off = b_off[p];
-        d.out_off = a_off[p] + b_off[p] + p;
+        d.a_off = a_off[p] - a0;
+        d.b_off = b_off[p] - b0;
+        d.out_off = d.a_off + d.b_off + p;
         d.dir_off = 0;
         d.la = static_cast<uint32_t>(la);
         d.lb = static_cast<uint32_t>(lb);
@@ -423,10 +486,27 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
         if(la % k != 0 || lb % k != 0) bt->host_status[p] = COATI_GPU_E_LENGTH;
     }
     // longest-processing-time order: biggest lattices first
-    std::stable_sort(bt->descs.begin(), bt->descs.end(), [](const PairDesc& x, const PairDesc& y) {
-        if(x.cfg != y.cfg) return x.cfg > y.cfg;
-        return (uint64_t)x.la * x.lb > (uint64_t)y.la * y.lb;
-    });
+    // (stable counting sort on a bucketed key: kernel config, then lattice size to ~1.6 % -- LPT does
+    // not need an exact order and a comparison sort of 1 M descriptors costs ~100 ms of host time)
+    {
+        auto bucket = [](const PairDesc& d) -> uint32_t {
+            const uint64_t cells = (uint64_t)d.la * d.lb + 1;
+            const int lz = 63 - __builtin_clzll(cells);
+            const uint32_t mant = lz >= 6 ? (uint32_t)((cells >> (lz - 6)) & 63) : (uint32_t)(cells << (6 - lz)) & 63;
+            const uint32_t size_rank = 4095u - (uint32_t)(lz * 64 + mant);  // bigger lattice first
+            // config rank: wave pairs first, then by R descending (any fixed order works)
+            const uint32_t cfg_rank = (d.cfg & CFG_WAVE) ? 0u : 16u - std::min(15u, d.cfg & 0xffu);
+            return cfg_rank * 4096u + size_rank;
+        };
+        const uint32_t NB = 17u * 4096u;
+        std::vector<uint32_t> hist(NB + 1, 0);
+        std::vector<uint32_t> key(npairs);
+        for(size_t p = 0; p < npairs; ++p) ++hist[(key[p] = bucket(bt->descs[p])) + 1];
+        for(uint32_t x = 0; x < NB; ++x) hist[x + 1] += hist[x];
+        std::vector<PairDesc> sorted(npairs);
+        for(size_t p = 0; p < npairs; ++p) sorted[hist[key[p]]++] = bt->descs[p];
+        bt->descs.swap(sorted);
+    }
     // direction-buffer chunks
     size_t free_b = 0, total_b = 0;
     CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -435,7 +515,7 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
                            npairs * (sizeof(PairDesc) + sizeof(PairResult)) + (256ull << 20);
     uint64_t budget = ctx->dir_budget;
     if(budget == 0) {
-        budget = free_b > fixed ? static_cast<uint64_t>((free_b - fixed) * 0.85) : 0;
+        budget = free_b > fixed ? static_cast<uint64_t>((free_b - fixed) * 0.85 * budget_share) : 0;
     }
     uint64_t need_max = 0;
     {
@@ -536,8 +616,7 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
     }
     if(npairs) {
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_pairs.p, bt->descs.data(), npairs * sizeof(PairDesc),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                                    cudaMemcpyHostToDevice, bt->stream));  // descs outlive the copy (member)
     }
     *out = holder.release();
     return COATI_GPU_OK;
@@ -551,7 +630,7 @@ extern "C" int coati_gpu_batch_upload(coati_gpu_batch* bt, const uint8_t* a_all,
     if((bt->a_total && (!a_all || !anc_all)) || (bt->b_total && (!b_all || !des_all)))
         return COATI_GPU_E_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = bt->stream;
     if(bt->a_total) {
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_a.p, a_all, bt->a_total, cudaMemcpyHostToDevice, s));
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_anc.p, anc_all, bt->a_total, cudaMemcpyHostToDevice, s));
@@ -577,18 +656,26 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
     if(!bt) return COATI_GPU_E_ARG;
     coati_gpu_ctx* ctx = bt->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = bt->stream;
     const uint32_t n = static_cast<uint32_t>(bt->npairs);
     bt->launches = 0;
     if(n == 0) return COATI_GPU_OK;
     // reset results (status from host-side validation)
-    for(size_t p = 0; p < bt->npairs; ++p) {
-        PairResult r{};
-        r.status = bt->host_status[p];
-        bt->h_results[p] = r;
+    // reset the per-pair records: all-zero, then the (rare) pairs rejected by host-side validation
+    CU_TRY(ctx, cudaMemsetAsync(bt->d_results.p, 0, n * sizeof(PairResult), s));
+    if(!bt->rejected_known) {
+        for(size_t p = 0; p < bt->npairs; ++p)
+            if(bt->host_status[p] != COATI_GPU_OK) {
+                PairResult r{};
+                r.status = bt->host_status[p];
+                bt->h_init.push_back(r);
+                bt->rejected.push_back(static_cast<uint32_t>(p));
+            }
+        bt->rejected_known = true;
     }
-    CU_TRY(ctx, cudaMemcpyAsync(bt->d_results.p, bt->h_results.data(), n * sizeof(PairResult),
-                                cudaMemcpyHostToDevice, s));
+    for(size_t x = 0; x < bt->rejected.size(); ++x)
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_results.p + bt->rejected[x], &bt->h_init[x], sizeof(PairResult),
+                                    cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemsetAsync(bt->d_counters.p, 0, bt->d_counters.n * sizeof(unsigned int), s));
     {
         const uint32_t warps_per_block = 8;
@@ -677,19 +764,27 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
     return COATI_GPU_OK;
 }
 
-extern "C" int coati_gpu_batch_download(coati_gpu_batch* bt, char* out_a, char* out_b,
-                                        uint64_t* out_len, float* score, int32_t* status) {
-    if(!bt) return COATI_GPU_E_ARG;
+static int batch_download_async(coati_gpu_batch* bt, char* out_a, char* out_b) {
     coati_gpu_ctx* ctx = bt->ctx;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = bt->stream;
     if(bt->npairs == 0) return COATI_GPU_OK;
     if(out_a)
         CU_TRY(ctx, cudaMemcpyAsync(out_a, bt->d_out_a.p, bt->out_total, cudaMemcpyDeviceToHost, s));
     if(out_b)
         CU_TRY(ctx, cudaMemcpyAsync(out_b, bt->d_out_b.p, bt->out_total, cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaMemcpyAsync(bt->h_results.data(), bt->d_results.p,
-                                bt->npairs * sizeof(PairResult), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(bt->h_results, bt->d_results.p, bt->npairs * sizeof(PairResult),
+                                cudaMemcpyDeviceToHost, s));
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_batch_download(coati_gpu_batch* bt, char* out_a, char* out_b,
+                                        uint64_t* out_len, float* score, int32_t* status) {
+    if(!bt) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = bt->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = bt->stream;
+    if(bt->npairs == 0) return COATI_GPU_OK;
+    if(int rc = batch_download_async(bt, out_a, out_b)) return rc;
     CU_TRY(ctx, cudaStreamSynchronize(s));
     for(size_t p = 0; p < bt->npairs; ++p) {
         const PairResult& r = bt->h_results[p];
@@ -715,7 +810,7 @@ extern "C" int coati_gpu_batch_timing(coati_gpu_batch* bt, double* fill_ms, doub
     if(!bt) return COATI_GPU_E_ARG;
     coati_gpu_ctx* ctx = bt->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(bt->stream));
     double f = 0, t = 0, c = 0;
     for(size_t ri = 0; 4 * ri + 3 < bt->events.size(); ++ri) {
         float ms = 0;
@@ -748,7 +843,7 @@ extern "C" int coati_gpu_batch_device_buffers(coati_gpu_batch* bt, void** out_a,
 extern "C" void coati_gpu_batch_destroy(coati_gpu_batch* bt) {
     if(!bt) return;
     cudaSetDevice(bt->ctx->device);
-    cudaStreamSynchronize(bt->ctx->stream);
+    cudaStreamSynchronize(bt->stream);
     delete bt;
 }
 
@@ -757,13 +852,56 @@ extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const 
                                        const uint64_t* b_off, const char* anc_all,
                                        const char* des_all, char* out_a, char* out_b,
                                        uint64_t* out_len, float* score, int32_t* status) {
-    coati_gpu_batch* bt = nullptr;
-    int rc = coati_gpu_batch_create(ctx, npairs, a_off, b_off, &bt);
-    if(rc != COATI_GPU_OK) return rc;
-    rc = coati_gpu_batch_upload(bt, a_all, b_all, anc_all, des_all);
-    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt);
-    if(rc == COATI_GPU_OK) rc = coati_gpu_batch_download(bt, out_a, out_b, out_len, score, status);
-    coati_gpu_batch_destroy(bt);
+    if(!ctx || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
+    // Large batches are cut into sub-batches that alternate between two streams, so that the host-side
+    // planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its neighbours.
+    const size_t kMinPipe = 32768;
+    size_t nsub = 1;
+    if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(8, npairs / kMinPipe);
+    if(const char* env = std::getenv("COATI_GPU_NSUB")) nsub = std::max(1, std::atoi(env));  // tuning
+    if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
+    coati_gpu_batch* bt[2] = {nullptr, nullptr};
+    size_t first[2] = {0, 0};
+    auto finish = [&](int slot) -> int {
+        coati_gpu_batch* b = bt[slot];
+        if(!b) return COATI_GPU_OK;
+        bt[slot] = nullptr;
+        int rc = COATI_GPU_OK;
+        if(cudaStreamSynchronize(b->stream) != cudaSuccess) {
+            ctx->last_error = cudaGetErrorString(cudaGetLastError());
+            rc = COATI_GPU_E_CUDA;
+        }
+        for(size_t p = 0; rc == COATI_GPU_OK && p < b->npairs; ++p) {
+            const PairResult& r = b->h_results[p];
+            if(out_len) out_len[first[slot] + p] = r.len;
+            if(score) score[first[slot] + p] = r.score;
+            if(status) status[first[slot] + p] = r.status;
+        }
+        delete b;  // stream already drained
+        return rc;
+    };
+    int rc = COATI_GPU_OK;
+    for(size_t j = 0; j < nsub && rc == COATI_GPU_OK; ++j) {
+        const int slot = (int)(j & 1);
+        rc = finish(slot);
+        if(rc != COATI_GPU_OK) break;
+        const size_t p0 = npairs * j / nsub, p1 = npairs * (j + 1) / nsub;
+        first[slot] = p0;
+        rc = batch_create_on(ctx, slot ? ctx->stream2 : ctx->stream, nsub > 1 ? 0.5 : 1.0, p1 - p0,
+                             a_off + p0, b_off + p0, &bt[slot]);
+        if(rc != COATI_GPU_OK) break;
+        const uint64_t ao = npairs ? a_off[p0] : 0, bo = npairs ? b_off[p0] : 0;
+        rc = coati_gpu_batch_upload(bt[slot], a_all ? a_all + ao : nullptr, b_all ? b_all + bo : nullptr,
+                                    anc_all ? anc_all + ao : nullptr, des_all ? des_all + bo : nullptr);
+        if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt[slot]);
+        if(rc == COATI_GPU_OK)
+            rc = batch_download_async(bt[slot], out_a ? out_a + ao + bo + p0 : nullptr,
+                                      out_b ? out_b + ao + bo + p0 : nullptr);
+    }
+    for(int slot = 0; slot < 2; ++slot) {
+        const int r2 = finish(slot);
+        if(rc == COATI_GPU_OK) rc = r2;
+    }
     return rc;
 }
 
