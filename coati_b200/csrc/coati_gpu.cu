@@ -22,6 +22,7 @@
 #include "viterbi_generic.cuh"
 #include "viterbi_pipe.cuh"
 #include "viterbi_pipe1.cuh"
+#include "viterbi_pipe3.cuh"
 
 using namespace coati_gpu;
 
@@ -209,10 +210,15 @@ PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false)
     return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, nullptr, viterbi_pipe1_kernel<R, WAVE, NC>,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
 }
+template <int R, int NC>
+PipeCfg make_cfg3() {  // K = 3: FADD2 specialisation (viterbi_pipe3.cuh)
+    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, nullptr, viterbi_pipe3_kernel<R, NC>,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
+}
 PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false, 16>(), make_cfg1<8, false, 16>(), make_cfg<3, 3>(),
-                         make_cfg<3, 6>(),          make_cfg1<2, true, 16>(),  make_cfg1<4, true, 16>(),
+                         make_cfg3<6, 16>(),        make_cfg1<2, true, 16>(),  make_cfg1<4, true, 16>(),
                          make_cfg1<8, true, 16>(),  make_cfg1<4, false, 4>(),  make_cfg1<8, false, 4>(),
-                         make_cfg1<8, true, 4>()};
+                         make_cfg1<8, true, 4>(),   make_cfg3<6, 4>()};
 
 // nc = 4 picks the ACGT-only variant when it exists, else falls back to the 16-column kernel
 const PipeCfg* find_cfg(uint32_t k, uint32_t cfg, uint32_t nc = 16) {
@@ -310,6 +316,9 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
         if(env[0] == '1') {
             g_pipe_cfgs[0].fn = viterbi_pipe_kernel<1, 4>, g_pipe_cfgs[0].fn1 = nullptr;
             g_pipe_cfgs[1].fn = viterbi_pipe_kernel<1, 8>, g_pipe_cfgs[1].fn1 = nullptr;
+            g_pipe_cfgs[3].fn = viterbi_pipe_kernel<3, 6>, g_pipe_cfgs[3].fn1 = nullptr;
+            g_pipe_cfgs[3].smem = (size_t)PIPE_WARPS * 2 * 16 * 32 * sizeof(float4);
+            g_pipe_cfgs[10].k = 0;  // disable the ACGT-only K = 3 variant as well
         }
     }
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';

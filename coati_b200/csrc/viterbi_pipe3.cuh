@@ -1,0 +1,193 @@
+// K = 3 (codon-unit gaps, `-k 3`) specialisation of the register-pipelined inter-pair Viterbi fill:
+// the scheme, the decision-plane stream (PipeLayout) and the exactness argument of viterbi_pipe.cuh,
+// with the issue-slot tuning of viterbi_pipe1.cuh (packed add.rn.f32x2 for the match/insert halves of
+// row pairs, FSETP + predicated IMAD for the decisions, lane 31 carrying lane 0's inputs).
+//
+// What K = 3 changes (src/lib/align_pair.cc:97-124 with look_back = 3):
+//   D(r, c) comes from row r-3: the three bottom rows of a lane go to the lane below (3 shuffles),
+//   I(r, c) comes from column c-3: a 3-deep history of Z per row,
+//   the fill adds ge*(k-1) / ge*k (S::power) where traceback compares with +ge only
+//   (align_pair.cc:285-296), so the decision maxima and the fill maxima are separate.
+#pragma once
+
+#include "common.cuh"
+#include "viterbi_pipe.cuh"
+#include "viterbi_pipe1.cuh"
+
+namespace coati_gpu {
+
+#define COATI_ROW3(q, xmq, ymq, zmq, xiq, yiq, ziq, zmkq, ikq)                                \
+    {                                                                                        \
+        const float D = (q) < 3 ? recvY[(q) < 3 ? (q) : 0] : Ycur[(q) >= 3 ? (q)-3 : 0];     \
+        const float xd = D + g.gs, yd = D + g.ge;                                            \
+        const float X = fmaxf(fmaxf(xmq, xd), xiq);                                          \
+        const float Yd = fmaxf(fmaxf(ymq, yd), yiq);                                         \
+        or_if_eq(acc[q][0], xmq, X, bm, one);                                                \
+        or_if_eq(acc[q][1], xd, X, bm, one);                                                 \
+        or_if_eq(acc[q][2], ymq, Yd, bm, one);                                               \
+        or_if_eq(acc[q][3], yd, Yd, bm, one);                                                \
+        or_if_gt(acc[q][4], zmq, ziq, bm, one);                                              \
+        Xp[q] = X;                                                                           \
+        Ycur[q] = fmaxf(fmaxf(ymq, yiq) + g.gk1, D + g.gk);                                  \
+        Zh[q][2] = Zh[q][1];                                                                 \
+        Zh[q][1] = Zh[q][0];                                                                 \
+        Zh[q][0] = fmaxf(zmkq, ikq);                                                         \
+    }
+
+template <int R, int NC>
+__global__ void __launch_bounds__(PIPE_WARPS * 32)
+viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+                     unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
+                     const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
+                     float4* __restrict__ bnd_all, uint32_t bnd_stride, uint8_t* __restrict__ dirs,
+                     PairResult* __restrict__ results, uint32_t* __restrict__) {
+    static_assert(R % 6 == 0, "rows are processed in pairs and handed over in threes");
+    constexpr int K = 3;
+    constexpr int R4 = (R + 3) / 4;
+    constexpr int H = 32 * R;
+    constexpr uint32_t WPL = (5 * R + 3) & ~3u;
+    extern __shared__ float4 s_dyn[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* s_tab = s_dyn + (size_t)warp * R4 * NC * 32;
+    float4* bnd = bnd_all + ((size_t)blockIdx.x * PIPE_WARPS + warp) * 2 * bnd_stride;
+    const uint32_t FULL = 0xffffffffu;
+    const int rot = (lane + 31) & 31;
+    const f2 ng2 = mk2(g.ng, g.ng), go2 = mk2(g.go, g.go), gs2 = mk2(g.gs, g.gs), ge2 = mk2(g.ge, g.ge);
+    const f2 gk12 = mk2(g.gk1, g.gk1), gk2 = mk2(g.gk, g.gk);
+    const char* tab_lane = reinterpret_cast<const char*>(s_tab) + lane * 16;
+    const uint32_t one = g.k / 3;  // == 1, opaque to the compiler (keeps the accumulate an IMAD)
+
+    for(;;) {
+        uint32_t p = 0;
+        if(lane == 0) p = first + atomicAdd(counter, 1u);
+        p = __shfl_sync(FULL, p, 0);
+        if(p >= last) break;
+        const PairDesc pd = pairs[p];
+        if(results[pd.orig].status != 0 || pd.la == 0 || pd.lb == 0) continue;
+        const uint32_t la = pd.la, lb = pd.lb;
+        const uint8_t* a = a_all + pd.a_off;
+        const uint8_t* b = b_all + pd.b_off;
+        uint4* dir = reinterpret_cast<uint4*>(dirs + pd.dir_off);
+        const uint32_t nblocks = pipe_nblocks(lb);
+        const uint32_t nbands = (la + H - 1) / H;
+        const uint32_t nsteps = lb + 31;
+
+        // rows above band 0: top margin row r = 0 (align_pair.cc:88-90) and two padding rows
+        for(uint32_t c = 1 + lane; c <= lb; c += 32) {
+            const CellOut o = cell_out<K>(LOWEST, LOWEST, margin_ins<K>(c, g), g);
+            bnd[c] = make_float4(o.X, LOWEST, LOWEST, o.Y);
+        }
+        __syncwarp();
+
+        for(uint32_t band = 0; band < nbands; ++band) {
+            const float4* bin = bnd + (size_t)(band & 1) * bnd_stride;
+            float4* bout = bnd + (size_t)((band + 1) & 1) * bnd_stride;
+            const uint32_t r0 = band * H + lane * R + 1;
+#pragma unroll
+            for(int h = 0; h < R4; ++h) {
+                float rowv[4][NC];
+#pragma unroll
+                for(int x = 0; x < 4; ++x) {
+                    const uint32_t r = r0 + 4 * h + x;
+                    const bool ok = (4 * h + x < R) && r <= la;
+                    const uint32_t code = ok ? a[r - 1] : 0;
+#pragma unroll
+                    for(int n = 0; n < NC; ++n) rowv[x][n] = ok ? table[code * TABLE_LD + n] : 0.0f;
+                }
+#pragma unroll
+                for(int n = 0; n < NC; ++n)
+                    s_tab[(h * NC + n) * 32 + lane] = make_float4(rowv[0][n], rowv[1][n], rowv[2][n], rowv[3][n]);
+            }
+            float Xp[R], Zh[R][K], Ycur[R], diagX, recvY[K];
+            uint32_t acc[R][5];
+#pragma unroll
+            for(int q = 0; q < R; ++q) {
+                Xp[q] = margin_del<K>(r0 + q, g) + g.gs;
+                Ycur[q] = 0.f;
+#pragma unroll
+                for(int z = 0; z < K; ++z) Zh[q][z] = LOWEST;
+#pragma unroll
+                for(int j = 0; j < 5; ++j) acc[q][j] = 0;
+            }
+            diagX = r0 == 1 ? (0.0f + g.ng) + g.ng : margin_del<K>(r0 - 1, g) + g.gs;
+            float outX = 0.f, outY0 = 0.f, outY1 = 0.f, outY2 = 0.f;
+            uint32_t boff = 0;
+            if(lane == 31) {
+                const float4 v = bin[1];
+                outX = v.x, outY0 = v.y, outY1 = v.z, outY2 = v.w;
+                boff = (uint32_t)b[0] * 512u;
+            }
+            uint32_t u = 0u - (uint32_t)lane;
+            __syncwarp();
+
+            for(uint32_t t = 0; t < nsteps; ++t, ++u) {
+                const float recvX = __shfl_sync(FULL, outX, rot);
+                recvY[0] = __shfl_sync(FULL, outY0, rot);
+                recvY[1] = __shfl_sync(FULL, outY1, rot);
+                recvY[2] = __shfl_sync(FULL, outY2, rot);
+                const uint32_t bo = __shfl_sync(FULL, boff, rot);
+                const uint32_t cn = min(t + 2, lb);
+                const float4 bnv = bin[cn];
+                const uint32_t bl = b[cn - 1];
+                if(u < lb) {
+                    const uint32_t bm = 1u << (31 - (t & 31));
+                    float sv[R4 * 4];
+#pragma unroll
+                    for(int h = 0; h < R4; ++h) {
+                        const float4 v = *reinterpret_cast<const float4*>(tab_lane + bo + h * (NC * 512));
+                        sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
+                    }
+                    float dXq = diagX;
+#pragma unroll
+                    for(int q = 0; q < R; q += 2) {
+                        const f2 M2 = add2(mk2(dXq, Xp[q]), mk2(sv[q], sv[q + 1]));
+                        const f2 I2 = mk2(Zh[q][K - 1], Zh[q + 1][K - 1]);
+                        const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2);
+                        const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2);
+                        const f2 zmk = add2(zm, gk12), ik = add2(I2, gk2);  // fill terms (:106-118)
+                        dXq = Xp[q + 1];
+                        COATI_ROW3(q, lo2(xm), lo2(ym), lo2(zm), lo2(xi), lo2(yi), lo2(zi), lo2(zmk), lo2(ik))
+                        COATI_ROW3(q + 1, hi2(xm), hi2(ym), hi2(zm), hi2(xi), hi2(yi), hi2(zi), hi2(zmk), hi2(ik))
+                    }
+                    outX = Xp[R - 1];
+                    outY0 = Ycur[R - 3], outY1 = Ycur[R - 2], outY2 = Ycur[R - 1];
+                    diagX = recvX;
+                    if(lane == 31) bout[u + 1] = make_float4(outX, outY0, outY1, outY2);
+                }
+                boff = bo;
+                if(lane == 31) {
+                    outX = bnv.x, outY0 = bnv.y, outY1 = bnv.z, outY2 = bnv.w;
+                    boff = bl * 512u;
+                }
+                if((t & 31) == 31 || t == nsteps - 1) {
+                    uint4* dst = dir + ((size_t)(band * nblocks + (t >> 5)) * 32 + lane) * (WPL / 4);
+                    uint32_t w[WPL];
+#pragma unroll
+                    for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
+#pragma unroll
+                    for(int x = 0; x < (int)WPL / 4; ++x)
+                        dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
+#pragma unroll
+                    for(int q = 0; q < R; ++q)
+#pragma unroll
+                        for(int j = 0; j < 5; ++j) acc[q][j] = 0;
+                }
+            }
+            if(band == nbands - 1) {
+                const uint32_t rr = (la - 1) % H;
+                if((uint32_t)lane == rr / R) {
+                    float score = 0.f;
+#pragma unroll
+                    for(int q = 0; q < R; ++q)
+                        if((uint32_t)q == rr % R) score = Xp[q];
+                    results[pd.orig].score = score;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+#undef COATI_ROW3
+
+}  // namespace coati_gpu
