@@ -569,7 +569,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
             if(s < c.last && bt->descs[s].cfg) max_lb_pipe = std::max(max_lb_pipe, bt->descs[s].lb);
         }
     }
-    bt->bnd_stride = (max_lb_pipe + 2 + 7) & ~7u;
+    bt->bnd_stride = (max_lb_pipe + 2 + 32 + 7) & ~7u;  // + 32: the step loop reads ahead past column lb
     bt->bnd_ctas = 0;
     uint64_t wave_f4 = 0;
     uint32_t wave_bands = 0;
@@ -605,7 +605,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
         if(e == cudaSuccess) e = r;
     };
     ok(bt->d_a.alloc(bt->a_total + 1, &ctx->pool));
-    ok(bt->d_b.alloc(bt->b_total + 1, &ctx->pool));
+    ok(bt->d_b.alloc(bt->b_total + 64, &ctx->pool));  // symbol read-ahead of the step loop
     ok(bt->d_anc.alloc(bt->a_total + 1, &ctx->pool));
     ok(bt->d_des.alloc(bt->b_total + 1, &ctx->pool));
     ok(bt->d_out_a.alloc(bt->out_total + 1, &ctx->pool));
