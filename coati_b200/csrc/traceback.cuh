@@ -38,18 +38,22 @@ struct PipeLayoutR {
         const uint32_t band = (r - 1) / H, rr = (r - 1) % H, lane = rr / R, q = rr % R;
         const uint32_t t = (c - 1) + lane, nblocks = (pd.lb + 62) / 32;
         shift = 31 - (t & 31);
-        return ((uint64_t)(band * nblocks + (t >> 5)) * 32 + lane) * WPL + q * 5;
+        // one widening multiply; the in-block part stays 32-bit
+        return (uint64_t)(band * nblocks + (t >> 5)) * (32u * WPL) + (lane * WPL + q * 5);
     }
     __device__ __forceinline__ static int next(const uint8_t* dir, const PairDesc& pd, int st,
                                                uint32_t r, uint32_t c) {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(dir);
         uint32_t sh;
         const uint64_t idx = word_index(pd, r, c, sh);
-        if(st == ST_I) return ((__ldg(w + idx + 4) >> sh) & 1u) ? ST_M : ST_I;
-        const uint32_t base = st == ST_M ? 0 : 2;
-        const uint32_t w0 = __ldg(w + idx + base), w1 = __ldg(w + idx + base + 1);  // independent loads
-        if((w0 >> sh) & 1u) return ST_M;
-        return ((w1 >> sh) & 1u) ? ST_D : ST_I;
+        // planes 0,1 (arrived by MATCH), 2,3 (DELETION) or 4 (INSERTION); both words are fetched
+        // together so the second never waits for the first
+        const uint32_t* q = w + idx + (st == ST_M ? 0 : st == ST_D ? 2 : 3);
+        uint32_t w0, w1;
+        asm volatile("ld.global.nc.u32 %0, [%2];\n\tld.global.nc.u32 %1, [%2+4];" : "=r"(w0), "=r"(w1) : "l"(q));
+        const uint32_t b0 = (w0 >> sh) & 1u, b1 = (w1 >> sh) & 1u;
+        if(st == ST_I) return b1 ? ST_M : ST_I;       // q -> planes 3,4: plane 4 is w1
+        return b0 ? ST_M : (b1 ? ST_D : ST_I);
     }
     // touch the cache lines holding the decisions of cell (r, c) (warp-cooperative read-ahead)
     __device__ __forceinline__ static uint32_t touch(const uint8_t* dir, const PairDesc& pd, uint32_t r,
@@ -128,6 +132,31 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
     }
     int err = 0;
     uint32_t nstep = 0, sink = 0;
+    if(k == 1 && la > 0 && lb > 0) {
+        // Lean walk for gap unit 1 (a single warp runs dependent code at ~6 cycles per instruction, so
+        // the step is kept to: emit, move, index, two loads, decode).  Inside the lattice body every
+        // move is legal; on a margin only one state is finite (align_pair.cc:84-90), so the rest of
+        // the path is emitted in bulk.
+        for(;;) {
+            --pos;
+            if(lead) ops[pos] = (char)st;
+            r -= (st != ST_I);
+            c -= (st != ST_D);
+            if(r == 0 || c == 0) break;
+            if(WARP && (nstep++ & 7) == 0) {
+                const uint32_t ahead = 64 + 8 * lane;
+                if(r > ahead && c > ahead) sink ^= Layout::touch(dir, pd, r - ahead, c - ahead);
+            }
+            st = Layout::next(dir, pd, st, r, c);
+        }
+        if(lead) {
+            for(; c > 0; --c) ops[--pos] = ST_I;  // top margin: insertions only
+            for(; r > 0; --r) ops[--pos] = ST_D;  // left margin: deletions only
+        } else {
+            pos -= r + c;
+        }
+        r = c = 0;
+    }
     while(r > 0 || c > 0) {  // :268  (j > k-1 || i > k-1)
         if(WARP && (nstep++ & 7) == 0) {
             const uint32_t ahead = 64 + 8 * lane;
