@@ -11,8 +11,9 @@ omega=0.5 pi=0.25 t=0.05, k=1, seed 42 -- PER GPU (weak scaling: rank r takes pa
 
 value  : whole-job GCUPS with inputs resident in HBM (CUDA events on the context's stream,
          max over ranks)
-e2e    : same metric through the C ABI call a user makes (coati_gpu_viterbi_batch) with pinned
-         HOST buffers: plan + H2D + kernels + D2H inside the timed region
+e2e    : same metric through the C ABI call a user makes (coati_gpu_alignpair_batch: raw sequences
+         in, aligned rows out) with pinned HOST buffers: validation + plan + H2D + encode + kernels +
+         D2H inside the timed region
 roofline / cpu_baseline: see DESIGN.md "Measurement".
 """
 from __future__ import annotations
@@ -300,12 +301,13 @@ def main():
 
     # ---- end-to-end through the public C ABI with host buffers -----------------------------------
     def e2e_once():
-        ctx._check(ctx.lib.coati_gpu_viterbi_batch(
-            ctx.h, npairs, w["a_all"].ctypes.data, w["a_off"].ctypes.data_as(coati_b200.capi._u64p),
-            w["b_all"].ctypes.data, w["b_off"].ctypes.data_as(coati_b200.capi._u64p),
-            w["anc_all"].ctypes.data, w["des_all"].ctypes.data, out_a.ctypes.data, out_b.ctypes.data,
-            out_len.ctypes.data_as(coati_b200.capi._u64p), score.ctypes.data_as(coati_b200.capi._fp),
-            status.ctypes.data_as(coati_b200.capi._i32p)))
+        # the call a user makes: raw sequences in, aligned rows + scores out (marg_alignment semantics:
+        # length checks, end-stop trim/restore, encoding on the device, Viterbi, traceback)
+        ctx._check(ctx.lib.coati_gpu_alignpair_batch(
+            ctx.h, npairs, w["anc_all"].ctypes.data, w["a_off"].ctypes.data_as(coati_b200.capi._u64p),
+            w["des_all"].ctypes.data, w["b_off"].ctypes.data_as(coati_b200.capi._u64p),
+            out_a.ctypes.data, out_b.ctypes.data, out_len.ctypes.data_as(coati_b200.capi._u64p),
+            score.ctypes.data_as(coati_b200.capi._fp), status.ctypes.data_as(coati_b200.capi._i32p)))
 
     batch.destroy()
     e2e_once()                                  # warm-up (allocations, page faults)
@@ -317,7 +319,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    h2d = int(2 * (w["a_off"][-1] + w["b_off"][-1]))
+    assert int((status != 0).sum()) == 0 and int(out_len.min()) > 0, "e2e run failed"
+    h2d = int(w["a_off"][-1] + w["b_off"][-1])
     d2h = int(2 * out_total + npairs * 32)
 
     # ---- reduce over ranks ------------------------------------------------------------------------

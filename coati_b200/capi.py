@@ -54,6 +54,7 @@ def load_library() -> C.CDLL:
                                       C.c_char_p, C.c_char_p, C.POINTER(C.c_size_t), _fp]
     lib.coati_gpu_viterbi_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, vp, vp,
                                             _u64p, _fp, _i32p]
+    lib.coati_gpu_alignpair_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, _u64p, _fp, _i32p]
     lib.coati_gpu_batch_create.argtypes = [vp, C.c_size_t, _u64p, _u64p, C.POINTER(vp)]
     lib.coati_gpu_batch_upload.argtypes = [vp, vp, vp, vp, vp]
     lib.coati_gpu_batch_run.argtypes = [vp]
@@ -317,6 +318,34 @@ class Context:
         out = np.empty_like(x)
         self._check(self.lib.coati_gpu_libm_eval(self.h, op, x.ctypes.data_as(_fp), out.ctypes.data_as(_fp), x.size))
         return out
+
+    def alignpair_batch(self, ancs, dess):
+        """marg_alignment semantics for a list of raw pairs.  Returns (rows_a, rows_b, scores, status)."""
+        n = len(ancs)
+        la = np.fromiter((len(x) for x in ancs), dtype=np.uint64, count=n)
+        lb = np.fromiter((len(x) for x in dess), dtype=np.uint64, count=n)
+        a_off = np.zeros(n + 1, dtype=np.uint64)
+        b_off = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(la, out=a_off[1:])
+        np.cumsum(lb, out=b_off[1:])
+        anc_all = np.frombuffer(("".join(ancs) + "\0").encode("latin-1"), dtype=np.uint8).copy()
+        des_all = np.frombuffer(("".join(dess) + "\0").encode("latin-1"), dtype=np.uint8).copy()
+        total = int(a_off[-1] + b_off[-1]) + n
+        out_a = np.zeros(total + 1, dtype=np.uint8)
+        out_b = np.zeros(total + 1, dtype=np.uint8)
+        out_len = np.zeros(n, dtype=np.uint64)
+        score = np.zeros(n, dtype=np.float32)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.coati_gpu_alignpair_batch(
+            self.h, n, _vp(anc_all), a_off.ctypes.data_as(_u64p), _vp(des_all), b_off.ctypes.data_as(_u64p),
+            _vp(out_a), _vp(out_b), out_len.ctypes.data_as(_u64p), score.ctypes.data_as(_fp),
+            status.ctypes.data_as(_i32p)))
+        rows_a, rows_b = [], []
+        for p in range(n):
+            o, ln = int(a_off[p] + b_off[p]) + p, int(out_len[p])
+            rows_a.append(out_a[o:o + ln].tobytes().decode("latin-1"))
+            rows_b.append(out_b[o:o + ln].tobytes().decode("latin-1"))
+        return rows_a, rows_b, score, status
 
     def batch(self, a_off, b_off) -> Batch:
         return Batch(self, a_off, b_off)

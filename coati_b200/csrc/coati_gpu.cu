@@ -259,6 +259,7 @@ struct coati_gpu_batch {
     DevBuf<uint32_t> d_prog;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
     uint32_t nc = 16;  // 4 when every descendant symbol of the batch is A/C/G/T (set at upload)
+    bool raw = false;  // raw-sequence batch: symbols are encoded on the device
     PairResult* h_results = nullptr;    // D2H landing zone (pinned, from ctx->hpool)
     std::vector<PairResult> h_init;     // records of the pairs rejected by host-side validation
     std::vector<uint32_t> rejected;     // their indices (caller order)
@@ -394,6 +395,7 @@ extern "C" int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float
     c.gk1 = c.ge * static_cast<float>(static_cast<size_t>(k - 1));  // semiring.hpp:109-111
     c.gk = c.ge * static_cast<float>(static_cast<size_t>(k));
     c.k = k;
+    c.stop_gap = ::logf(g * e * e);  // utils.cc:1049
     std::vector<float> padded(TABLE_ROWS * TABLE_LD, 0.0f);
     for(int r = 0; r < TABLE_ROWS; ++r)
         for(int col = 0; col < TABLE_COLS; ++col)
@@ -422,8 +424,11 @@ __global__ void validate_symbols_kernel(const PairDesc* __restrict__ pairs, uint
         results[pd.orig].status = COATI_GPU_E_SYMBOL;
 }
 
+// raw: optional per-pair byte {bit0: ancestor ends with a stop codon, bit1: descendant does, bit7: the
+// pair fails the length checks of process_marginal} for the raw-sequence entry point
 static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
-                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out);
+                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out,
+                           const uint8_t* raw = nullptr);
 
 extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const uint64_t* a_off,
                                       const uint64_t* b_off, coati_gpu_batch** out) {
@@ -434,7 +439,8 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
 // offsets may start anywhere (a sub-range of a larger CSR pack): everything is stored relative to
 // a_off[0] / b_off[0]
 static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
-                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out) {
+                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out,
+                           const uint8_t* raw) {
     if(!ctx || !out || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
     if(!ctx->model_set || npairs > 0xfffffff0ull) return COATI_GPU_E_ARG;
     *out = nullptr;
@@ -460,8 +466,14 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
     bt->out_total = bt->a_total + bt->b_total + npairs;
     for(size_t p = 0; p < npairs; ++p) {
         PairDesc& d = bt->descs[p];
-        const uint64_t la = a_off[p + 1] - a_off[p], lb = b_off[p + 1] - b_off[p];
+        uint64_t la = a_off[p + 1] - a_off[p], lb = b_off[p + 1] - b_off[p];
         if(la > 0x7fffffffull || lb > 0x7fffffffull) return COATI_GPU_E_ARG;
+        uint32_t stop_bits = 0;
+        if(raw) {  // lengths after trim_end_stops; the slots keep their full size
+            if(raw[p] & 0x80) bt->host_status[p] = COATI_GPU_E_LENGTH;
+            if(raw[p] & 1) la -= 3, stop_bits |= CFG_STOP_A;
+            if(raw[p] & 2) lb -= 3, stop_bits |= CFG_STOP_B;
+        }
         d.a_off = a_off[p] - a0;
         d.b_off = b_off[p] - b0;
         d.out_off = d.a_off + d.b_off + p;
@@ -486,14 +498,16 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
                 // measured on B200 (tools/wave_exp.py): the systolic chain is latency bound per step, so
                 // the widest lane tile wins at every length from 10k to 160k
                 (void)nb8, (void)nb4;
-                d.cfg = 8u | CFG_WAVE;
+                d.cfg = (la <= 100000 ? 4u : 8u) | CFG_WAVE;
                 if(ctx->wave_r) d.cfg = ctx->wave_r | CFG_WAVE;
             }
         }
         // the reference checks divisibility before trimming stops (utils.cc:819-837); a lattice
         // whose terminal cell is unreachable is undefined behaviour upstream -> reject here.
         if(la % k != 0 || lb % k != 0) bt->host_status[p] = COATI_GPU_E_LENGTH;
+        d.cfg |= stop_bits;
     }
+    bt->raw = raw != nullptr;
     // longest-processing-time order: biggest lattices first
     // (stable counting sort on a bucketed key: kernel config, then lattice size to ~1.6 % -- LPT does
     // not need an exact order and a comparison sort of 1 M descriptors costs ~100 ms of host time)
@@ -534,7 +548,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
             const bool live = bt->host_status[d.orig] == COATI_GPU_OK;
             const uint64_t cells = live ? (uint64_t)d.la * d.lb : 0;
             const uint64_t bytes = !live || cells == 0 ? 0
-                                   : d.cfg ? pipe_dir_bytes(d.la, d.lb, d.cfg & 0xffu) : cells;
+                                   : (d.cfg & 0x1ffu) ? pipe_dir_bytes(d.la, d.lb, d.cfg & 0xffu) : cells;
             const uint64_t padded = (bytes + 127) & ~127ull;
             if(padded > budget) {
                 ctx->last_error = "direction stream of one pair exceeds device memory budget";
@@ -561,12 +575,12 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
         const Chunk& c = bt->chunks[ci];
         uint32_t s0 = c.first;
         for(uint32_t s = c.first; s <= c.last; ++s) {
-            if(s == c.last || bt->descs[s].cfg != bt->descs[s0].cfg ||
+            if(s == c.last || (bt->descs[s].cfg & 0x1ffu) != (bt->descs[s0].cfg & 0x1ffu) ||
                (bt->descs[s0].cfg & CFG_WAVE)) {
-                if(s > s0) bt->runs.push_back(Run{s0, s, bt->descs[s0].cfg, (uint32_t)ci});
+                if(s > s0) bt->runs.push_back(Run{s0, s, bt->descs[s0].cfg & 0x1ffu, (uint32_t)ci});
                 s0 = s;
             }
-            if(s < c.last && bt->descs[s].cfg) max_lb_pipe = std::max(max_lb_pipe, bt->descs[s].lb);
+            if(s < c.last && (bt->descs[s].cfg & 0x1ffu)) max_lb_pipe = std::max(max_lb_pipe, bt->descs[s].lb);
         }
     }
     bt->bnd_stride = (max_lb_pipe + 2 + 32 + 7) & ~7u;  // + 32: the step loop reads ahead past column lb
@@ -636,6 +650,17 @@ extern "C" int coati_gpu_batch_upload(coati_gpu_batch* bt, const uint8_t* a_all,
                                       const char* des_all) {
     if(!bt) return COATI_GPU_E_ARG;
     coati_gpu_ctx* ctx = bt->ctx;
+    if(bt->raw) {  // raw-sequence batch: only the symbols travel; codes are produced on the device
+        if((bt->a_total && !anc_all) || (bt->b_total && !des_all)) return COATI_GPU_E_ARG;
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        cudaStream_t s = bt->stream;
+        if(bt->a_total)
+            CU_TRY(ctx, cudaMemcpyAsync(bt->d_anc.p, anc_all, bt->a_total, cudaMemcpyHostToDevice, s));
+        if(bt->b_total)
+            CU_TRY(ctx, cudaMemcpyAsync(bt->d_des.p, des_all, bt->b_total, cudaMemcpyHostToDevice, s));
+        bt->nc = 16;
+        return COATI_GPU_OK;
+    }
     if((bt->a_total && (!a_all || !anc_all)) || (bt->b_total && (!b_all || !des_all)))
         return COATI_GPU_E_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -688,9 +713,20 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
     CU_TRY(ctx, cudaMemsetAsync(bt->d_counters.p, 0, bt->d_counters.n * sizeof(unsigned int), s));
     {
         const uint32_t warps_per_block = 8;
-        validate_symbols_kernel<<<(n + warps_per_block - 1) / warps_per_block,
-                                  warps_per_block * 32, 0, s>>>(bt->d_pairs.p, n, bt->d_a.p,
-                                                                 bt->d_b.p, bt->d_results.p);
+        if(bt->raw) {
+            // the counters buffer has one spare word: used as the "any ambiguity code" flag
+            unsigned int* flag = bt->d_counters.p + bt->runs.size();
+            encode_pairs_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                                  s>>>(bt->d_pairs.p, n, bt->d_anc.p, bt->d_des.p, bt->d_a.p, bt->d_b.p,
+                                       bt->d_results.p, flag);
+            unsigned int h_flag = 1;
+            CU_TRY(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaStreamSynchronize(s));  // only this sub-batch's H2D + encode are waited on
+            bt->nc = h_flag ? 16 : 4;
+        } else
+            validate_symbols_kernel<<<(n + warps_per_block - 1) / warps_per_block,
+                                      warps_per_block * 32, 0, s>>>(bt->d_pairs.p, n, bt->d_a.p,
+                                                                     bt->d_b.p, bt->d_results.p);
         ++bt->launches;
     }
     if(bt->events.size() != 4 * bt->runs.size()) {
@@ -764,7 +800,7 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
         cudaEventRecord(ev[2], s);
         expand_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last, bt->d_anc.p,
                                                          bt->d_des.p, bt->d_out_a.p, bt->d_out_b.p,
-                                                         bt->d_results.p);
+                                                         bt->d_results.p, ctx->gap.stop_gap);
         cudaEventRecord(ev[3], s);
         bt->launches += 3;
     }
@@ -856,11 +892,10 @@ extern "C" void coati_gpu_batch_destroy(coati_gpu_batch* bt) {
     delete bt;
 }
 
-extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
-                                       const uint64_t* a_off, const uint8_t* b_all,
-                                       const uint64_t* b_off, const char* anc_all,
-                                       const char* des_all, char* out_a, char* out_b,
-                                       uint64_t* out_len, float* score, int32_t* status) {
+static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                              const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
+                              const char* anc_all, const char* des_all, char* out_a, char* out_b,
+                              uint64_t* out_len, float* score, int32_t* status, const uint8_t* raw) {
     if(!ctx || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
     // Large batches are cut into sub-batches that alternate between two streams, so that the host-side
     // planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its neighbours.
@@ -897,7 +932,7 @@ extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const 
         const size_t p0 = npairs * j / nsub, p1 = npairs * (j + 1) / nsub;
         first[slot] = p0;
         rc = batch_create_on(ctx, slot ? ctx->stream2 : ctx->stream, nsub > 1 ? 0.5 : 1.0, p1 - p0,
-                             a_off + p0, b_off + p0, &bt[slot]);
+                             a_off + p0, b_off + p0, &bt[slot], raw ? raw + p0 : nullptr);
         if(rc != COATI_GPU_OK) break;
         const uint64_t ao = npairs ? a_off[p0] : 0, bo = npairs ? b_off[p0] : 0;
         rc = coati_gpu_batch_upload(bt[slot], a_all ? a_all + ao : nullptr, b_all ? b_all + bo : nullptr,
@@ -912,6 +947,59 @@ extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const 
         if(rc == COATI_GPU_OK) rc = r2;
     }
     return rc;
+}
+
+extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                       const uint64_t* a_off, const uint8_t* b_all,
+                                       const uint64_t* b_off, const char* anc_all,
+                                       const char* des_all, char* out_a, char* out_b,
+                                       uint64_t* out_len, float* score, int32_t* status) {
+    return viterbi_batch_impl(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
+                              out_len, score, status, nullptr);
+}
+
+// marg_alignment (align_marginal.cc:44-88) for a batch of raw pairs: process_marginal's length checks
+// (before trimming, utils.cc:819-837), trim_end_stops, marginal_seq_encoding (on the device),
+// viterbi_mem + traceback_viterbi, restore_end_stops.
+extern "C" int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, const char* anc_all,
+                                         const uint64_t* anc_off, const char* des_all,
+                                         const uint64_t* des_off, char* out_a, char* out_b,
+                                         uint64_t* out_len, float* score, int32_t* status) {
+    if(!ctx || (npairs && (!anc_off || !des_off || !anc_all || !des_all))) return COATI_GPU_E_ARG;
+    if(!ctx->model_set) return COATI_GPU_E_ARG;
+    std::vector<uint8_t> raw;
+    try {
+        raw.assign(npairs, 0);
+    } catch(const std::bad_alloc&) {
+        return COATI_GPU_E_NOMEM;
+    }
+    const uint32_t k = ctx->gap.k;
+    auto nuc = [](char ch) -> int {
+        switch(ch) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        default: return -1;
+        }
+    };
+    auto ends_with_stop = [&](const char* s, uint64_t len) {  // utils.cc:945-967 via cod_int
+        if(len < 3) return false;
+        const int n0 = nuc(s[len - 3]), n1 = nuc(s[len - 2]), n2 = nuc(s[len - 1]);
+        if((n0 | n1 | n2) < 0) return false;
+        const int cod = (n0 << 4) | (n1 << 2) | n2;
+        return cod == 48 || cod == 50 || cod == 56;
+    };
+    for(size_t p = 0; p < npairs; ++p) {
+        const uint64_t la = anc_off[p + 1] - anc_off[p], lb = des_off[p + 1] - des_off[p];
+        uint8_t f = 0;
+        if(la % 3 != 0 || la % k != 0 || lb % k != 0) f |= 0x80;
+        if(ends_with_stop(anc_all + anc_off[p], la)) f |= 1;
+        if(ends_with_stop(des_all + des_off[p], lb)) f |= 2;
+        raw[p] = f;
+    }
+    return viterbi_batch_impl(ctx, npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b,
+                              out_len, score, status, raw.data());
 }
 
 extern "C" int coati_gpu_viterbi(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
@@ -968,7 +1056,7 @@ extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a
             const uint64_t n = La * Lb;
             const PairDesc pd = bt->descs[0];
             const unsigned grid = (unsigned)((n + 255) / 256);
-            if(pd.cfg)
+            if(pd.cfg & 0x1ffu)
                 unpack_dirs_kernel<PipeLayout><<<grid, 256, 0, ctx->stream>>>(bt->d_dirs.p, pd, rowmajor.p);
             else
                 unpack_dirs_kernel<DiagLayout><<<grid, 256, 0, ctx->stream>>>(bt->d_dirs.p, pd, rowmajor.p);

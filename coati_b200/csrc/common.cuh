@@ -30,6 +30,7 @@ struct GapConsts {
     float gk1;  // ge * float(k-1)
     float gk;   // ge * float(k)
     uint32_t k;
+    float stop_gap;  // logf(g * e * e): restore_end_stops penalty (utils.cc:1049)
 };
 
 // One alignment task.  Offsets are in bytes/symbols from the start of the batch arenas.
@@ -46,6 +47,9 @@ struct PairDesc {
 };
 
 constexpr uint32_t CFG_WAVE = 0x100u;
+// raw-sequence entry point: a terminal stop codon was trimmed from the ancestor / descendant
+// (utils.cc:945-967) and is put back by expand_rows_kernel (utils.cc:1044-1063)
+constexpr uint32_t CFG_STOP_A = 0x10000u, CFG_STOP_B = 0x20000u;
 
 // Per-pair results (device side, caller order).
 struct PairResult {

@@ -212,7 +212,7 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
 __global__ void expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                                    const char* __restrict__ anc_all, const char* __restrict__ des_all,
                                    char* __restrict__ out_a, char* __restrict__ out_b,
-                                   const PairResult* __restrict__ results) {
+                                   PairResult* __restrict__ results, float stop_gap) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t p = first + warp;
     if(p >= last) return;
@@ -222,7 +222,8 @@ __global__ void expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t 
     const char* des = des_all + pd.b_off;
     char* oa = out_a + pd.out_off;
     char* ob = out_b + pd.out_off;
-    const uint32_t n = res.status == 0 ? res.len : 0, shift = res.start;
+    uint32_t n = res.status == 0 ? res.len : 0;
+    const uint32_t shift = res.start;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t ia = 0, ib = 0;
     for(uint32_t base = 0; base < n; base += 32) {
@@ -242,9 +243,94 @@ __global__ void expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t 
         ib += __popc(mb);
         __syncwarp();
     }
+    // restore_end_stops (utils.cc:1044-1063): both / neither -> append as they were; only one -> the
+    // codon opposite "---" and the gap penalty log(g * e * e) added to the score
+    const bool sa = pd.cfg & CFG_STOP_A, sb = pd.cfg & CFG_STOP_B;
+    if(res.status == 0 && (sa || sb)) {
+        if(lane < 3) {
+            oa[n + lane] = sa ? anc[pd.la + lane] : '-';
+            ob[n + lane] = sb ? des[pd.lb + lane] : '-';
+        }
+        if(lane == 0) {
+            results[pd.orig].len = n + 3;
+            if(sa != sb) results[pd.orig].score = res.score + stop_gap;
+        }
+        n += 3;
+    }
     if(lane == 0) {
         oa[n] = 0;
         ob[n] = 0;
+    }
+}
+
+// Raw-sequence entry point: marginal_seq_encoding (utils.cc:496-528) on the device, one warp per pair.
+// anc -> codon61 * 3 + phase (any symbol outside ACGTUacgtu: E_AMBIGUOUS; an in-frame stop codon:
+// E_STOP), des -> IUPAC code (codes 15 / 16, i.e. '-' or anything else: E_SYMBOL, where the reference
+// would index past the table).  pd.la / pd.lb are the lengths after end-stop trimming.
+__device__ __forceinline__ uint32_t nt16_code(unsigned char ch) {
+    switch(ch | 0x20) {  // case-insensitive for letters
+    case 'a': return 0;
+    case 'c': return 1;
+    case 'g': return 2;
+    case 't': case 'u': return 3;
+    case 'r': return 4;
+    case 'y': return 5;
+    case 'm': return 6;
+    case 'k': return 7;
+    case 's': return 8;
+    case 'w': return 9;
+    case 'b': return 10;
+    case 'd': return 11;
+    case 'h': return 12;
+    case 'v': return 13;
+    case 'n': return 14;
+    default: return ch == '-' ? 15 : 16;
+    }
+}
+
+__global__ void encode_pairs_kernel(const PairDesc* __restrict__ pairs, uint32_t npairs,
+                                    const char* __restrict__ anc_all, const char* __restrict__ des_all,
+                                    uint8_t* __restrict__ a_all, uint8_t* __restrict__ b_all,
+                                    PairResult* __restrict__ results,
+                                    uint32_t* __restrict__ any_ambiguity_code) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(warp >= npairs) return;
+    const PairDesc pd = pairs[warp];
+    if(results[pd.orig].status != 0) return;
+    const char* anc = anc_all + pd.a_off;
+    const char* des = des_all + pd.b_off;
+    uint8_t* a = a_all + pd.a_off;
+    uint8_t* b = b_all + pd.b_off;
+    // first offending ancestor codon decides the error, as the reference's loop does (utils.cc:504-515)
+    uint32_t first_bad = 0xffffffffu;  // (codon index << 2) | 1: ambiguous, | 2: stop
+    bool bad_des = false, beyond_acgt = false;
+    for(uint32_t cod = lane; cod * 3 < pd.la; cod += 32) {
+        const uint32_t n0 = nt16_code(anc[3 * cod]), n1 = nt16_code(anc[3 * cod + 1]),
+                       n2 = nt16_code(anc[3 * cod + 2]);
+        uint32_t c61 = 0;
+        if((n0 | n1 | n2) > 3) {
+            first_bad = min(first_bad, (cod << 2) | 1u);
+        } else {
+            const uint32_t c64 = (n0 << 4) | (n1 << 2) | n2;
+            if(c64 == 48 || c64 == 50 || c64 == 56) first_bad = min(first_bad, (cod << 2) | 2u);
+            c61 = c64 < 48 ? c64 : c64 == 49 ? 48 : c64 < 57 ? c64 - 2 : c64 - 3;  // utils.cc:1144-1165
+        }
+        a[3 * cod] = (uint8_t)(3 * c61);
+        a[3 * cod + 1] = (uint8_t)(3 * c61 + 1);
+        a[3 * cod + 2] = (uint8_t)(3 * c61 + 2);
+    }
+    for(uint32_t x = lane; x < pd.lb; x += 32) {
+        const uint32_t code = nt16_code(des[x]);
+        if(code > 14) bad_des = true;
+        if(code > 3) beyond_acgt = true;
+        b[x] = (uint8_t)(code > 14 ? 0 : code);
+    }
+    if(__any_sync(0xffffffffu, beyond_acgt) && lane == 0) *any_ambiguity_code = 1u;  // benign race
+    for(int o = 16; o > 0; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+    bad_des = __any_sync(0xffffffffu, bad_des);
+    if(lane == 0) {
+        if(first_bad != 0xffffffffu) results[pd.orig].status = (first_bad & 1u) ? -6 : -7;
+        else if(bad_des) results[pd.orig].status = -4;
     }
 }
 

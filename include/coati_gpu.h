@@ -80,6 +80,19 @@ int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_
                             const char* anc_all, const char* des_all, char* out_a, char* out_b,
                             uint64_t* out_len, float* score, int32_t* status);
 
+/* ---- alignpair, batch of RAW pairs -----------------------------------------------------------------
+ * = marg_alignment (align_marginal.cc:44-88) per pair, minus file I/O: the length checks of
+ * process_marginal (La % 3, La % k, Lb % k, on the untrimmed sequences, utils.cc:819-837), trim_end_stops
+ * (utils.cc:945-967), marginal_seq_encoding (utils.cc:496-528, here on the device), viterbi_mem +
+ * traceback_viterbi, restore_end_stops (utils.cc:1044-1063).  Inputs are the raw symbols only (CSR);
+ * outputs as for coati_gpu_viterbi_batch (rows at anc_off[p] + des_off[p] + p).  Per-pair status:
+ * COATI_GPU_E_LENGTH / E_AMBIGUOUS / E_STOP carry the reference's exception messages; E_SYMBOL marks a
+ * descendant symbol outside the IUPAC table (undefined behaviour upstream). */
+int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, const char* anc_all,
+                              const uint64_t* anc_off, const char* des_all, const uint64_t* des_off,
+                              char* out_a, char* out_b, uint64_t* out_len, float* score,
+                              int32_t* status);
+
 /* Staged form of the same call, so the device-resident part can be timed alone:
  *   create  : host-side plan (length-binned LPT order, direction-buffer chunks) + device buffers
  *   upload  : H2D of sequences        run : fill + traceback kernels only (async on the stream)

@@ -225,3 +225,42 @@ def test_wavefront_kernel_equals_inter_pair_kernel(tables):
         ctx.close()
     for got in outs:
         assert got[:2] == want[:2] and util.f32_bits(got[2]) == util.f32_bits(want[2])
+
+
+def test_alignpair_batch_raw_sequences(gpu_ctx, tables):
+    """coati_gpu_alignpair_batch = marg_alignment per pair (length checks before trimming, end-stop
+    trim/restore with its score penalty, encoding on the device) against the oracle pipeline."""
+    rng = np.random.RandomState(77)
+    T = tables["mg_golden"]
+    g, e = oracle.DEFAULT_G, oracle.DEFAULT_E
+    for k in (1, 3):
+        gpu_ctx.set_model(T, g, e, k)
+        ancs, dess = [], []
+        stops = ["TAA", "TAG", "TGA", "taa", "UAG", ""]
+        for i in range(48):
+            anc, des = util.random_pair(rng, int(rng.randint(1, 70)), k=k, ambiguous=i % 6 == 0)
+            anc, _ = oracle.trim_end_stop(anc)
+            des, _ = oracle.trim_end_stop(des)
+            ancs.append(anc + stops[i % 6])
+            dess.append(des + stops[(i // 2) % 6])
+        # error cases, each reported per pair without disturbing the others
+        ancs += ["AAACCNGGG", "AAATAAGGG", "AAATAGCCNGGG", "AAACCC", "AAAC", "AAACCC"]
+        dess += ["AAACCC", "AAACCC", "AAACCC", "AA-CCC", "AAA", "AAACC" if k == 3 else "AAAC?C"]
+        want_status = [0] * 48 + [-6, -7, -7, -4, -5, -5 if k == 3 else -4]
+        rows_a, rows_b, score, status = gpu_ctx.alignpair_batch(ancs, dess)
+        assert list(status) == want_status
+        for p in range(48):
+            at, s0 = oracle.trim_end_stop(ancs[p])
+            dt, s1 = oracle.trim_end_stop(dess[p])
+            oa, ob, osc = oracle.viterbi(at, dt, T, g, e, k)
+            oa, ob, osc = oracle.restore_end_stops(oa, ob, osc, (s0, s1), g, e)
+            assert (rows_a[p], rows_b[p]) == (oa, ob), p
+            assert util.f32_bits(score[p]) == util.f32_bits(osc), p
+        assert all(rows_a[p] == "" for p in range(48, 54))
+    # the reference's own driver cases (align_marginal.cc:149-240)
+    gpu_ctx.set_model(T, g, e, 1)
+    ra, rb, _, st = gpu_ctx.alignpair_batch(["CTCTGGATAGTG", "GCGACTGTT", "ACGTTAAGGGGT"],
+                                            ["CTATAGTG", "GCGATTGCTGTT", "ACGAAT"])
+    assert list(st) == [0, 0, 0]
+    assert list(zip(ra, rb)) == [("CTCTGGATAGTG", "CT----ATAGTG"), ("GCGA---CTGTT", "GCGATTGCTGTT"),
+                                 ("ACGTTAAGGGGT", "ACG--AA----T")]
