@@ -50,6 +50,9 @@ def load_library() -> C.CDLL:
     lib.coati_gpu_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.coati_gpu_set_model.argtypes = [vp, _fp, C.c_float, C.c_float, C.c_uint32]
+    lib.coati_gpu_set_models.argtypes = [vp, C.c_uint32, _fp, C.c_float, C.c_float, C.c_uint32]
+    lib.coati_gpu_viterbi_batch_models.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp,
+                                                   C.POINTER(C.c_uint32), vp, vp, _u64p, _fp, _i32p]
     lib.coati_gpu_viterbi.argtypes = [vp, _u8p, C.c_size_t, _u8p, C.c_size_t, C.c_char_p, C.c_char_p,
                                       C.c_char_p, C.c_char_p, C.POINTER(C.c_size_t), _fp]
     lib.coati_gpu_viterbi_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, vp, vp,
@@ -292,8 +295,17 @@ class Context:
                                                C.byref(ol), C.byref(sc)))
         return oa.raw[:ol.value].decode("latin-1"), ob.raw[:ol.value].decode("latin-1"), np.float32(sc.value)
 
-    def viterbi_batch(self, pack: PackedPairs):
+    def set_models(self, tables, gap_open=0.001, gap_extend=1.0 - 1.0 / 6.0, gap_len=1):
+        t = np.ascontiguousarray(tables, dtype=np.float32)
+        assert t.ndim == 3 and t.shape[1:] == (183, 15)
+        self._check(self.lib.coati_gpu_set_models(self.h, t.shape[0], t.ctypes.data_as(_fp), np.float32(gap_open),
+                                                  np.float32(gap_extend), int(gap_len)))
+        self.k = int(gap_len)
+
+    def viterbi_batch(self, pack: PackedPairs, model_idx=None):
         """Returns (rows_a, rows_b, scores float32[n], status int32[n]) in input order."""
+        if model_idx is not None:
+            return self._viterbi_batch_models(pack, model_idx)
         out_a = np.zeros(pack.out_total + 1, dtype=np.uint8)
         out_b = np.zeros(pack.out_total + 1, dtype=np.uint8)
         out_len = np.zeros(pack.n, dtype=np.uint64)
@@ -303,6 +315,25 @@ class Context:
             self.h, pack.n, _vp(pack.a_all), pack.a_off.ctypes.data_as(_u64p), _vp(pack.b_all),
             pack.b_off.ctypes.data_as(_u64p), _vp(pack.anc_all), _vp(pack.des_all), _vp(out_a), _vp(out_b),
             out_len.ctypes.data_as(_u64p), score.ctypes.data_as(_fp), status.ctypes.data_as(_i32p)))
+        rows_a, rows_b = [], []
+        for p in range(pack.n):
+            o, n = int(pack.out_off[p]), int(out_len[p])
+            rows_a.append(out_a[o:o + n].tobytes().decode("latin-1"))
+            rows_b.append(out_b[o:o + n].tobytes().decode("latin-1"))
+        return rows_a, rows_b, score, status
+
+    def _viterbi_batch_models(self, pack: PackedPairs, model_idx):
+        m = np.ascontiguousarray(model_idx, dtype=np.uint32)
+        out_a = np.zeros(pack.out_total + 1, dtype=np.uint8)
+        out_b = np.zeros(pack.out_total + 1, dtype=np.uint8)
+        out_len = np.zeros(pack.n, dtype=np.uint64)
+        score = np.zeros(pack.n, dtype=np.float32)
+        status = np.zeros(pack.n, dtype=np.int32)
+        self._check(self.lib.coati_gpu_viterbi_batch_models(
+            self.h, pack.n, _vp(pack.a_all), pack.a_off.ctypes.data_as(_u64p), _vp(pack.b_all),
+            pack.b_off.ctypes.data_as(_u64p), _vp(pack.anc_all), _vp(pack.des_all),
+            m.ctypes.data_as(C.POINTER(C.c_uint32)), _vp(out_a), _vp(out_b), out_len.ctypes.data_as(_u64p),
+            score.ctypes.data_as(_fp), status.ctypes.data_as(_i32p)))
         rows_a, rows_b = [], []
         for p in range(pack.n):
             o, n = int(pack.out_off[p]), int(out_len[p])

@@ -122,7 +122,8 @@ struct coati_gpu_ctx {
     cudaDeviceProp prop{};
     bool model_set = false;
     GapConsts gap{};
-    float* d_table = nullptr;  // TABLE_ROWS x TABLE_LD
+    float* d_table = nullptr;  // n_models x TABLE_ROWS x TABLE_LD
+    uint32_t n_models = 1, table_cap = 1;
     uint64_t launches = 0;
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
@@ -382,9 +383,9 @@ extern "C" int coati_gpu_device_info(coati_gpu_ctx* ctx, int* sm_count, int* clo
     return COATI_GPU_OK;
 }
 
-extern "C" int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float g, float e,
-                                   uint32_t k) {
-    if(!ctx || !table || k == 0) return COATI_GPU_E_ARG;
+extern "C" int coati_gpu_set_models(coati_gpu_ctx* ctx, uint32_t n_models, const float* tables, float g,
+                                    float e, uint32_t k) {
+    if(!ctx || !tables || k == 0 || n_models == 0 || n_models > CFG_MAX_MODELS) return COATI_GPU_E_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     // align_pair.cc:66-69 -- host libm, float, same calls as the reference
     GapConsts c;
@@ -396,16 +397,34 @@ extern "C" int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float
     c.gk = c.ge * static_cast<float>(static_cast<size_t>(k));
     c.k = k;
     c.stop_gap = ::logf(g * e * e);  // utils.cc:1049
-    std::vector<float> padded(TABLE_ROWS * TABLE_LD, 0.0f);
-    for(int r = 0; r < TABLE_ROWS; ++r)
-        for(int col = 0; col < TABLE_COLS; ++col)
-            padded[r * TABLE_LD + col] = table[r * TABLE_COLS + col];
+    if(n_models > ctx->table_cap) {
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
+        float* nt = nullptr;
+        CU_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&nt),
+                               (size_t)n_models * TABLE_ROWS * TABLE_LD * sizeof(float)));
+        cudaFree(ctx->d_table);
+        ctx->d_table = nt;
+        ctx->table_cap = n_models;
+    }
+    std::vector<float> padded((size_t)n_models * TABLE_ROWS * TABLE_LD, 0.0f);
+    for(uint32_t m = 0; m < n_models; ++m)
+        for(int r = 0; r < TABLE_ROWS; ++r)
+            for(int col = 0; col < TABLE_COLS; ++col)
+                padded[((size_t)m * TABLE_ROWS + r) * TABLE_LD + col] =
+                    tables[((size_t)m * TABLE_ROWS + r) * TABLE_COLS + col];
     CU_TRY(ctx, cudaMemcpyAsync(ctx->d_table, padded.data(), padded.size() * sizeof(float),
                                 cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->gap = c;
+    ctx->n_models = n_models;
     ctx->model_set = true;
     return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float g, float e,
+                                   uint32_t k) {
+    return coati_gpu_set_models(ctx, 1, table, g, e, k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,7 +447,7 @@ __global__ void validate_symbols_kernel(const PairDesc* __restrict__ pairs, uint
 // pair fails the length checks of process_marginal} for the raw-sequence entry point
 static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
                            const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out,
-                           const uint8_t* raw = nullptr);
+                           const uint8_t* raw = nullptr, const uint32_t* model = nullptr);
 
 extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const uint64_t* a_off,
                                       const uint64_t* b_off, coati_gpu_batch** out) {
@@ -440,7 +459,7 @@ extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const u
 // a_off[0] / b_off[0]
 static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
                            const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out,
-                           const uint8_t* raw) {
+                           const uint8_t* raw, const uint32_t* model) {
     if(!ctx || !out || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
     if(!ctx->model_set || npairs > 0xfffffff0ull) return COATI_GPU_E_ARG;
     *out = nullptr;
@@ -506,6 +525,10 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
         // whose terminal cell is unreachable is undefined behaviour upstream -> reject here.
         if(la % k != 0 || lb % k != 0) bt->host_status[p] = COATI_GPU_E_LENGTH;
         d.cfg |= stop_bits;
+        if(model) {
+            if(model[p] >= ctx->n_models) return COATI_GPU_E_ARG;
+            d.cfg |= model[p] << CFG_MODEL_SHIFT;
+        }
     }
     bt->raw = raw != nullptr;
     // longest-processing-time order: biggest lattices first
@@ -895,7 +918,8 @@ extern "C" void coati_gpu_batch_destroy(coati_gpu_batch* bt) {
 static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
                               const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
                               const char* anc_all, const char* des_all, char* out_a, char* out_b,
-                              uint64_t* out_len, float* score, int32_t* status, const uint8_t* raw) {
+                              uint64_t* out_len, float* score, int32_t* status, const uint8_t* raw,
+                              const uint32_t* model = nullptr) {
     if(!ctx || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
     // Large batches are cut into sub-batches that alternate between two streams, so that the host-side
     // planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its neighbours.
@@ -932,7 +956,8 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
         const size_t p0 = npairs * j / nsub, p1 = npairs * (j + 1) / nsub;
         first[slot] = p0;
         rc = batch_create_on(ctx, slot ? ctx->stream2 : ctx->stream, nsub > 1 ? 0.5 : 1.0, p1 - p0,
-                             a_off + p0, b_off + p0, &bt[slot], raw ? raw + p0 : nullptr);
+                             a_off + p0, b_off + p0, &bt[slot], raw ? raw + p0 : nullptr,
+                             model ? model + p0 : nullptr);
         if(rc != COATI_GPU_OK) break;
         const uint64_t ao = npairs ? a_off[p0] : 0, bo = npairs ? b_off[p0] : 0;
         rc = coati_gpu_batch_upload(bt[slot], a_all ? a_all + ao : nullptr, b_all ? b_all + bo : nullptr,
@@ -956,6 +981,19 @@ extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const 
                                        uint64_t* out_len, float* score, int32_t* status) {
     return viterbi_batch_impl(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
                               out_len, score, status, nullptr);
+}
+
+// The leaf batch of the msa driver (align_msa.cc:285-318): every pair names its own substitution model
+// (one table per branch length), gap parameters shared.
+extern "C" int coati_gpu_viterbi_batch_models(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                              const uint64_t* a_off, const uint8_t* b_all,
+                                              const uint64_t* b_off, const char* anc_all,
+                                              const char* des_all, const uint32_t* model_idx, char* out_a,
+                                              char* out_b, uint64_t* out_len, float* score,
+                                              int32_t* status) {
+    if(npairs && !model_idx) return COATI_GPU_E_ARG;
+    return viterbi_batch_impl(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
+                              out_len, score, status, nullptr, model_idx);
 }
 
 // marg_alignment (align_marginal.cc:44-88) for a batch of raw pairs: process_marginal's length checks

@@ -50,6 +50,8 @@ constexpr uint32_t CFG_WAVE = 0x100u;
 // raw-sequence entry point: a terminal stop codon was trimmed from the ancestor / descendant
 // (utils.cc:945-967) and is put back by expand_rows_kernel (utils.cc:1044-1063)
 constexpr uint32_t CFG_STOP_A = 0x10000u, CFG_STOP_B = 0x20000u;
+// substitution-model index of the pair (per-leaf branch lengths of the msa driver, align_msa.cc:285-318)
+constexpr uint32_t CFG_MODEL_SHIFT = 18, CFG_MAX_MODELS = 1u << 14;
 
 // Per-pair results (device side, caller order).
 struct PairResult {

@@ -399,9 +399,36 @@ subst_table_t marginal_p(const matrix61_t& P, const std::vector<float_t>& pi, Am
 }
 
 // ---- utils.cc:595-618 (marginal models) ---------------------------------------------------------------
+// ---- io.cc:48-88 ------------------------------------------------------------------------------------
+matrix61_t parse_matrix_csv(const std::string& file) {
+    std::ifstream input(file);
+    if(!input.good()) throw std::invalid_argument("Error opening file " + file + ".");
+    std::string line;
+    std::getline(input, line);
+    const float br_len = std::stof(line);
+    matrix61_t Q(N61 * N61, 0.f);
+    int count = 0;
+    while(std::getline(input, line)) {
+        std::stringstream ss(line);
+        std::string c0, c1, val;
+        std::getline(ss, c0, ',');
+        std::getline(ss, c1, ',');
+        std::getline(ss, val, ',');
+        const int cod0 = cod64_to_61(cod_int(c0)), cod1 = cod64_to_61(cod_int(c1));
+        Q[cod0 * N61 + cod1] = std::stof(val);
+        count++;
+    }
+    if(count != 3721) throw std::invalid_argument("Error reading substitution rate CSV file. Exiting!");
+    for(float& q : Q) q *= br_len;
+    matrix61_t P;
+    expm61(Q, P);
+    return P;
+}
+
 void set_subst(alignment_t& aln) {
     if(!aln.rate.empty()) {
-        throw std::invalid_argument("--sub rate matrices are not supported by this build.");
+        aln.model = "user_marg_model";
+        aln.subst_matrix = marginal_p(parse_matrix_csv(aln.rate), aln.pi, aln.amb, aln.sub);
     } else if(aln.model == "mar-ecm") {
         // NB marginalised with the caller's pi (MG94 default), not ecm_pi -- as upstream (:603-604)
         aln.subst_matrix = marginal_p(ecm_p(aln.br_len, aln.omega), aln.pi, aln.amb, aln.sub);
@@ -505,7 +532,75 @@ data_t read_fasta(std::istream& in) {  // fasta.cc:39-76
     return fasta;
 }
 
-data_t read_input(alignment_t& aln) {  // io.cc:184-222 (FASTA only in this build)
+data_t read_phylip(std::istream& in) {  // phylip.cc:37-97
+    data_t phylip;
+    std::string line;
+    in >> line;
+    const int n_seqs = std::stoi(line);
+    in >> line;
+    const int len_seqs = std::stoi(line);
+    (void)len_seqs;
+    phylip.names.resize(n_seqs);
+    phylip.seqs.resize(n_seqs);
+    auto strip = [](std::string s) {
+        s.erase(std::remove_if(s.begin(), s.end(), [](unsigned char c) { return std::isspace(c); }), s.end());
+        return s;
+    };
+    for(int i = 0; i < n_seqs; i++) {
+        std::getline(in, line);
+        if(line.empty()) std::getline(in, line);
+        phylip.names[i] = strip(line.substr(0, 10));
+        phylip.seqs[i] = line.size() > 10 ? strip(line.substr(10)) : std::string();
+    }
+    size_t count = 0;
+    while(in.good()) {
+        const size_t index = count % n_seqs;
+        std::getline(in, line);
+        if(line.empty()) continue;
+        phylip.seqs[index] += strip(line);
+        count++;
+    }
+    return phylip;
+}
+
+// json.cc:44-79: {"alignment": {name: seq, ...}, "score": x} -- a minimal reader for exactly the
+// documents COATi writes (string values without escapes other than \" and \\)
+data_t read_json(std::istream& in) {
+    std::stringstream buf;
+    buf << in.rdbuf();
+    const std::string t = buf.str();
+    data_t d;
+    size_t i = t.find("\"alignment\"");
+    if(i == std::string::npos) throw std::invalid_argument("Invalid JSON input: no \"alignment\" object.");
+    i = t.find('{', i);
+    const size_t end = t.find('}', i);
+    if(i == std::string::npos || end == std::string::npos) throw std::invalid_argument("Invalid JSON input.");
+    auto next_string = [&](size_t& pos, std::string& out) -> bool {
+        const size_t q0 = t.find('"', pos);
+        if(q0 == std::string::npos || q0 > end) return false;
+        out.clear();
+        size_t q = q0 + 1;
+        for(; q < t.size() && t[q] != '"'; ++q) {
+            if(t[q] == '\\' && q + 1 < t.size()) ++q;
+            out.push_back(t[q]);
+        }
+        pos = q + 1;
+        return true;
+    };
+    size_t pos = i + 1;
+    std::string key, val;
+    while(next_string(pos, key)) {
+        if(!next_string(pos, val)) throw std::invalid_argument("Invalid JSON input.");
+        d.names.push_back(key);
+        d.seqs.push_back(val);
+    }
+    const size_t sc = t.find("\"score\"", end);
+    if(sc == std::string::npos) throw std::invalid_argument("Invalid JSON input: no \"score\".");
+    d.score = std::stof(t.substr(t.find(':', sc) + 1));
+    return d;
+}
+
+data_t read_input(alignment_t& aln) {  // io.cc:184-222
     file_type_t t = aln.data.path.empty() ? file_type_t{"-", ".json"} : extract_file_type(aln.data.path);
     std::ifstream infile;
     std::istream* pin = &std::cin;
@@ -516,6 +611,8 @@ data_t read_input(alignment_t& aln) {  // io.cc:184-222 (FASTA only in this buil
     }
     data_t d;
     if(t.type_ext == ".fa" || t.type_ext == ".fasta") d = read_fasta(*pin);
+    else if(t.type_ext == ".phy") d = read_phylip(*pin);
+    else if(t.type_ext == ".json") d = read_json(*pin);
     else throw std::invalid_argument("Invalid input " + aln.data.path + ".");
     d.path = aln.data.path;
     return d;

@@ -63,7 +63,7 @@ struct alignment_t {
     std::vector<float_t> pi{0.308f, 0.185f, 0.199f, 0.308f};
     std::string refs;
     bool rev{false};
-    std::string rate;  // --sub CSV (not supported yet: SURVEY 8(f) item 4)
+    std::string rate;  // --sub: path to a CSV codon rate matrix (io.cc:48-88)
     gap_t gap;
     std::vector<float_t> sigma{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     subst_table_t subst_matrix;
@@ -106,6 +106,7 @@ matrix61_t ecm_p(float br_len, float omega);
 subst_table_t marginal_p(const matrix61_t& P, const std::vector<float_t>& pi, AmbiguousNucs amb,
                          MarginalSubst msub);
 void set_subst(alignment_t& aln);
+matrix61_t parse_matrix_csv(const std::string& file);  // io.cc:48-88
 // float Pade scaling-and-squaring matrix exponential (the algorithm of Eigen 3.4 MatrixBase::exp())
 void expm61(const matrix61_t& A, matrix61_t& out);
 
@@ -126,6 +127,8 @@ struct file_type_t {
 };
 file_type_t extract_file_type(std::string path);
 data_t read_fasta(std::istream& in);
+data_t read_phylip(std::istream& in);
+data_t read_json(std::istream& in);
 data_t read_input(alignment_t& aln);
 void write_fasta(const data_t& d, std::ostream& out);
 void write_phylip(const data_t& d, std::ostream& out);

@@ -35,10 +35,9 @@ viterbi_generic_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint3
                        uint8_t* __restrict__ dirs, PairResult* __restrict__ results) {
     __shared__ float s_table[TABLE_ROWS * TABLE_LD];
     __shared__ unsigned int s_pair;
-    for(int x = threadIdx.x; x < TABLE_ROWS * TABLE_LD; x += blockDim.x) s_table[x] = table[x];
     const uint32_t depth = ring_depth(g.k);
     float* ring = ring_all + (size_t)blockIdx.x * 3 * depth * ring_stride;
-    __syncthreads();
+    uint32_t cached_model = 0xffffffffu;
 
     for(;;) {
         if(threadIdx.x == 0) s_pair = first + atomicAdd(counter, 1u);
@@ -48,6 +47,12 @@ viterbi_generic_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint3
         if(p >= last) break;
         const PairDesc pd = pairs[p];
         if(results[pd.orig].status != 0) continue;
+        if((pd.cfg >> CFG_MODEL_SHIFT) != cached_model) {  // substitution table of this pair's model
+            cached_model = pd.cfg >> CFG_MODEL_SHIFT;
+            const float* tab = table + (size_t)cached_model * (TABLE_ROWS * TABLE_LD);
+            for(int x = threadIdx.x; x < TABLE_ROWS * TABLE_LD; x += blockDim.x) s_table[x] = tab[x];
+            __syncthreads();
+        }
         const uint32_t la = pd.la, lb = pd.lb, k = g.k;
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;

@@ -65,6 +65,7 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         const PairDesc pd = pairs[p];
         if(results[pd.orig].status != 0 || pd.la == 0 || pd.lb == 0) continue;
         const uint32_t la = pd.la, lb = pd.lb;
+        const float* tab = table + (size_t)(pd.cfg >> CFG_MODEL_SHIFT) * (TABLE_ROWS * TABLE_LD);
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;
         uint4* dir = reinterpret_cast<uint4*>(dirs + pd.dir_off);
@@ -92,7 +93,7 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     const bool ok = (4 * h + x < R) && r <= la;
                     const uint32_t code = ok ? a[r - 1] : 0;
 #pragma unroll
-                    for(int n = 0; n < NC; ++n) rowv[x][n] = ok ? table[code * TABLE_LD + n] : 0.0f;
+                    for(int n = 0; n < NC; ++n) rowv[x][n] = ok ? tab[code * TABLE_LD + n] : 0.0f;
                 }
 #pragma unroll
                 for(int n = 0; n < NC; ++n)

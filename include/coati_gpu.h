@@ -61,6 +61,11 @@ int coati_gpu_device_info(coati_gpu_ctx* ctx, int* sm_count, int* clock_khz, siz
 int coati_gpu_set_model(coati_gpu_ctx* ctx, const float* table, float gap_open, float gap_extend,
                         uint32_t gap_len);
 
+/* Several substitution models at once (tables: n_models x 183 x 15), gap parameters shared: the msa
+ * driver aligns every leaf with its own branch length (align_msa.cc:285-318: set_subst per leaf). */
+int coati_gpu_set_models(coati_gpu_ctx* ctx, uint32_t n_models, const float* tables, float gap_open,
+                         float gap_extend, uint32_t gap_len);
+
 /* ---- Viterbi, one pair ------------------------------------------------------------------------
  * = viterbi_mem (align_pair.cc:195-198) + traceback_viterbi (:319-323) as marg_alignment calls
  * them (align_marginal.cc:69-80).  out_a/out_b: caller buffers of >= La+Lb+1 bytes (NUL added). */
@@ -79,6 +84,13 @@ int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_
                             const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
                             const char* anc_all, const char* des_all, char* out_a, char* out_b,
                             uint64_t* out_len, float* score, int32_t* status);
+
+/* Same, every pair aligned under its own model of coati_gpu_set_models (model_idx[p] < n_models). */
+int coati_gpu_viterbi_batch_models(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                   const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
+                                   const char* anc_all, const char* des_all, const uint32_t* model_idx,
+                                   char* out_a, char* out_b, uint64_t* out_len, float* score,
+                                   int32_t* status);
 
 /* ---- alignpair, batch of RAW pairs -----------------------------------------------------------------
  * = marg_alignment (align_marginal.cc:44-88) per pair, minus file I/O: the length checks of

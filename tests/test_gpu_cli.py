@@ -105,3 +105,36 @@ def test_sample_failures(tmp_path):
     assert run("sample", fasta(tmp_path, ">A\nCCC\n>B\nCCCC\n"), "-k", "3").returncode != 0
     assert run("sample", fasta(tmp_path, ">A\nCCC\n")).returncode != 0
     assert run("sample", fasta(tmp_path, ">A\nCCC\n>B\nCCC\n"), "-o", "/nonexistent-dir/x.json").returncode != 0
+
+
+def test_phylip_and_json_input_and_sub_matrix(tmp_path, tables):
+    """io.cc:184-222 readers (read_input test cases, io.cc:226-306) and --sub (io.cc:48-88;
+    align_marginal.cc:304-344: a CSV of the MG94 Q gives the mar-mg alignment)."""
+    phy = tmp_path / "in.phy"
+    phy.write_text("2 12\n1         CTCTGGATAGTG\n2         CTATAGTG\n")
+    j = json.loads(run("alignpair", phy).stdout)
+    assert j["alignment"] == {"1": "CTCTGGATAGTG", "2": "CT----ATAGTG"}
+    js = tmp_path / "in.json"
+    js.write_text('{\n  "alignment": {\n    "a": "CTCTGGATAGTG",\n    "b": "CTATAGTG"\n  },\n  "score": 0.1\n}\n')
+    out = tmp_path / "o.fa"
+    assert run("alignpair", js, "-o", out).returncode == 0
+    assert out.read_text() == ">a\nCTCTGGATAGTG\n>b\nCT----ATAGTG\n"
+    # --sub: normalised MG94 Q (so that expm(Q * t) == mg94_p) written as codon,codon,value lines
+    from oracle import table as otable
+    Q, d = otable.mg94_q(0.2, otable.DEFAULT_PI)
+    Q = Q / d
+    codons = util.SENSE_CODONS
+    csv = tmp_path / "q.csv"
+    with open(csv, "w") as f:
+        f.write("0.0133\n")
+        for i in range(61):
+            for k in range(61):
+                f.write("%s,%s,%r\n" % (codons[i], codons[k], float(Q[i, k])))
+    f = fasta(tmp_path, ">1\nCTCTGGATAGTG\n>2\nCTATAGTG\n")
+    out = tmp_path / "sub.fasta"
+    r = run("alignpair", f, "--sub", csv, "-o", out)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == ">1\nCTCTGGATAGTG\n>2\nCT----ATAGTG\n"
+    bad = tmp_path / "bad.csv"
+    bad.write_text("0.0133\nAAA,AAA,0.1\n")
+    assert run("alignpair", f, "--sub", bad).returncode != 0

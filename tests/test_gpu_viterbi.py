@@ -264,3 +264,30 @@ def test_alignpair_batch_raw_sequences(gpu_ctx, tables):
     assert list(st) == [0, 0, 0]
     assert list(zip(ra, rb)) == [("CTCTGGATAGTG", "CT----ATAGTG"), ("GCGA---CTGTT", "GCGATTGCTGTT"),
                                  ("ACGTTAAGGGGT", "ACG--AA----T")]
+
+
+@pytest.mark.parametrize("k,force_generic", [(1, False), (3, False), (1, True)])
+def test_per_pair_models_leaf_batch(k, force_generic, tables):
+    """The msa leaf batch (align_msa.cc:285-318): each pair aligned with its own substitution table."""
+    import coati_b200
+    if force_generic:
+        os.environ["COATI_GPU_FORCE_GENERIC"] = "1"
+    try:
+        ctx = coati_b200.Context(0)
+    finally:
+        os.environ.pop("COATI_GPU_FORCE_GENERIC", None)
+    names = ["mg_golden", "ecm_default", "mg_c5"]
+    T = np.stack([tables[n] for n in names])
+    ctx.set_models(T, oracle.DEFAULT_G, oracle.DEFAULT_E, k)
+    rng = np.random.RandomState(31 + k)
+    ancs, dess, As, Bs = _random_batch(rng, 45, k, 80)
+    model = np.arange(45) % 3
+    rows_a, rows_b, score, status = ctx.viterbi_batch(PackedPairs(As, Bs, ancs, dess), model_idx=model)
+    assert (status == 0).all()
+    for p in range(45):
+        oa, ob, osc = oracle.viterbi(ancs[p], dess[p], tables[names[model[p]]], k=k, enc=(As[p], Bs[p]))
+        assert (rows_a[p], rows_b[p]) == (oa, ob), p
+        assert util.f32_bits(score[p]) == util.f32_bits(osc), p
+    with pytest.raises(coati_b200.CoatiGpuError):
+        ctx.viterbi_batch(PackedPairs(As[:2], Bs[:2], ancs[:2], dess[:2]), model_idx=[0, 3])
+    ctx.close()
