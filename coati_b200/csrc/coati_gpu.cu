@@ -13,6 +13,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +26,18 @@
 #include "viterbi_pipe3.cuh"
 
 using namespace coati_gpu;
+
+// COATI_GPU_TRACE=1: host-side timeline on stderr (ms since the first mark of the process)
+static bool trace_on() {
+    static const bool on = std::getenv("COATI_GPU_TRACE") != nullptr;
+    return on;
+}
+static void trace_mark(const char* what, size_t id) {
+    if(!trace_on()) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[coati_gpu trace] %9.2f ms  %-22s %zu\n", ms, what, id);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Grow-only device memory pool: batches borrow blocks and give them back, so repeated calls of the
@@ -118,7 +131,11 @@ struct HostPool {
 struct coati_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   // all work of the public staged API
-    cudaStream_t stream2 = nullptr;  // second lane of the pipelined coati_gpu_viterbi_batch
+    // lanes of the pipelined coati_gpu_viterbi_batch: the fills of lane i run on lane_fill[i] (default
+    // priority; lane_fill[0] == stream), everything else of the lane on the high-priority lane_hi[i]
+    static constexpr int NLANE = 3;
+    cudaStream_t lane_fill[NLANE] = {nullptr, nullptr, nullptr};
+    cudaStream_t lane_hi[NLANE] = {nullptr, nullptr, nullptr};
     cudaDeviceProp prop{};
     bool model_set = false;
     GapConsts gap{};
@@ -242,7 +259,8 @@ double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
 
 struct coati_gpu_batch {
     coati_gpu_ctx* ctx = nullptr;
-    cudaStream_t stream = nullptr;  // every operation of this batch is ordered on this stream
+    cudaStream_t stream = nullptr;  // every operation of this batch is ordered on this stream ...
+    cudaStream_t fill_stream = nullptr;  // ... except the fills, fenced by events when it is another stream
     size_t npairs = 0;
     uint64_t a_total = 0, b_total = 0, out_total = 0;
     std::vector<PairDesc> descs;  // sorted (largest lattice first)
@@ -303,12 +321,26 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     if(cudaSetDevice(device) != cudaSuccess ||
        cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
        cudaMalloc(reinterpret_cast<void**>(&ctx->d_table),
                   TABLE_ROWS * TABLE_LD * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return COATI_GPU_E_CUDA;
+    }
+    {
+        int least = 0, greatest = 0;
+        bool ok = cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
+        ctx->lane_fill[0] = ctx->stream;
+        for(int i = 0; ok && i < coati_gpu_ctx::NLANE; ++i) {
+            if(i > 0)
+                ok = cudaStreamCreateWithPriority(&ctx->lane_fill[i], cudaStreamNonBlocking, least) == cudaSuccess;
+            ok = ok && cudaStreamCreateWithPriority(&ctx->lane_hi[i], cudaStreamNonBlocking, greatest) == cudaSuccess;
+        }
+        if(!ok) {
+            cudaGetLastError();
+            coati_gpu_shutdown(ctx);
+            return COATI_GPU_E_CUDA;
+        }
     }
     if(const char* env = std::getenv("COATI_GPU_DIR_BUDGET_MB")) {
         ctx->dir_budget = static_cast<size_t>(std::strtoull(env, nullptr, 10)) << 20;
@@ -346,13 +378,17 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
 extern "C" void coati_gpu_shutdown(coati_gpu_ctx* ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
+    for(int i = 0; i < coati_gpu_ctx::NLANE; ++i) {
+        cudaStream_t both[2] = {ctx->lane_hi[i], i > 0 ? ctx->lane_fill[i] : nullptr};
+        for(cudaStream_t st : both)
+            if(st) {
+                cudaStreamSynchronize(st);
+                cudaStreamDestroy(st);
+            }
+    }
     if(ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
-    }
-    if(ctx->stream2) {
-        cudaStreamSynchronize(ctx->stream2);
-        cudaStreamDestroy(ctx->stream2);
     }
     if(ctx->d_table) cudaFree(ctx->d_table);
     ctx->pool.trim();
@@ -398,8 +434,7 @@ extern "C" int coati_gpu_set_models(coati_gpu_ctx* ctx, uint32_t n_models, const
     c.k = k;
     c.stop_gap = ::logf(g * e * e);  // utils.cc:1049
     if(n_models > ctx->table_cap) {
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
+        CU_TRY(ctx, cudaDeviceSynchronize());
         float* nt = nullptr;
         CU_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&nt),
                                (size_t)n_models * TABLE_ROWS * TABLE_LD * sizeof(float)));
@@ -445,21 +480,24 @@ __global__ void validate_symbols_kernel(const PairDesc* __restrict__ pairs, uint
 
 // raw: optional per-pair byte {bit0: ancestor ends with a stop codon, bit1: descendant does, bit7: the
 // pair fails the length checks of process_marginal} for the raw-sequence entry point
-static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
-                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out,
-                           const uint8_t* raw = nullptr, const uint32_t* model = nullptr);
+static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t fill_stream,
+                           uint64_t lane_budget, size_t npairs, const uint64_t* a_off,
+                           const uint64_t* b_off, coati_gpu_batch** out, const uint8_t* raw = nullptr,
+                           const uint32_t* model = nullptr);
 
 extern "C" int coati_gpu_batch_create(coati_gpu_ctx* ctx, size_t npairs, const uint64_t* a_off,
                                       const uint64_t* b_off, coati_gpu_batch** out) {
     if(!ctx) return COATI_GPU_E_ARG;
-    return batch_create_on(ctx, ctx->stream, 1.0, npairs, a_off, b_off, out);
+    return batch_create_on(ctx, ctx->stream, ctx->stream, 0, npairs, a_off, b_off, out);
 }
 
 // offsets may start anywhere (a sub-range of a larger CSR pack): everything is stored relative to
 // a_off[0] / b_off[0]
-static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budget_share, size_t npairs,
-                           const uint64_t* a_off, const uint64_t* b_off, coati_gpu_batch** out,
-                           const uint8_t* raw, const uint32_t* model) {
+// lane_budget: direction-stream bytes this batch may use (0 = derive from the free device memory)
+static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t fill_stream,
+                           uint64_t lane_budget, size_t npairs, const uint64_t* a_off,
+                           const uint64_t* b_off, coati_gpu_batch** out, const uint8_t* raw,
+                           const uint32_t* model) {
     if(!ctx || !out || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
     if(!ctx->model_set || npairs > 0xfffffff0ull) return COATI_GPU_E_ARG;
     *out = nullptr;
@@ -469,6 +507,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
     if(!bt) return COATI_GPU_E_NOMEM;
     bt->ctx = ctx;
     bt->stream = stream;
+    bt->fill_stream = fill_stream;
     bt->npairs = npairs;
     const uint32_t k = ctx->gap.k;
     const uint64_t a0 = npairs ? a_off[0] : 0, b0 = npairs ? b_off[0] : 0;
@@ -483,6 +522,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
     bt->a_total = npairs ? a_off[npairs] - a0 : 0;
     bt->b_total = npairs ? b_off[npairs] - b0 : 0;
     bt->out_total = bt->a_total + bt->b_total + npairs;
+    trace_mark("  plan: host alloc", npairs);
     for(size_t p = 0; p < npairs; ++p) {
         PairDesc& d = bt->descs[p];
         uint64_t la = a_off[p + 1] - a_off[p], lb = b_off[p + 1] - b_off[p];
@@ -531,6 +571,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
         }
     }
     bt->raw = raw != nullptr;
+    trace_mark("  plan: descs", npairs);
     // longest-processing-time order: biggest lattices first
     // (stable counting sort on a bucketed key: kernel config, then lattice size to ~1.6 % -- LPT does
     // not need an exact order and a comparison sort of 1 M descriptors costs ~100 ms of host time)
@@ -554,14 +595,15 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
         bt->descs.swap(sorted);
     }
     // direction-buffer chunks
-    size_t free_b = 0, total_b = 0;
-    CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-    free_b += ctx->pool.idle_bytes();
-    const uint64_t fixed = 2 * (bt->a_total + bt->b_total) + 2 * bt->out_total +
-                           npairs * (sizeof(PairDesc) + sizeof(PairResult)) + (256ull << 20);
-    uint64_t budget = ctx->dir_budget;
-    if(budget == 0) {
-        budget = free_b > fixed ? static_cast<uint64_t>((free_b - fixed) * 0.85 * budget_share) : 0;
+    trace_mark("  plan: sorted", npairs);
+    uint64_t budget = ctx->dir_budget ? ctx->dir_budget : lane_budget;
+    if(budget == 0) {  // (cudaMemGetInfo can block for tens of ms while kernels run: never inside the pipeline)
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->pool.idle_bytes();
+        const uint64_t fixed = 2 * (bt->a_total + bt->b_total) + 2 * bt->out_total +
+                               npairs * (sizeof(PairDesc) + sizeof(PairResult)) + (256ull << 20);
+        budget = free_b > fixed ? static_cast<uint64_t>((free_b - fixed) * 0.85) : 0;
     }
     uint64_t need_max = 0;
     {
@@ -641,6 +683,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
     auto ok = [&](cudaError_t r) {
         if(e == cudaSuccess) e = r;
     };
+    trace_mark("  plan: chunks+runs", npairs);
     ok(bt->d_a.alloc(bt->a_total + 1, &ctx->pool));
     ok(bt->d_b.alloc(bt->b_total + 64, &ctx->pool));  // symbol read-ahead of the step loop
     ok(bt->d_anc.alloc(bt->a_total + 1, &ctx->pool));
@@ -660,10 +703,12 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, double budge
         cudaGetLastError();
         return COATI_GPU_E_NOMEM;
     }
+    trace_mark("  plan: buffers", npairs);
     if(npairs) {
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_pairs.p, bt->descs.data(), npairs * sizeof(PairDesc),
                                     cudaMemcpyHostToDevice, bt->stream));  // descs outlive the copy (member)
     }
+    trace_mark("  plan: descs H2D", npairs);
     *out = holder.release();
     return COATI_GPU_OK;
 }
@@ -735,7 +780,7 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                     cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemsetAsync(bt->d_counters.p, 0, bt->d_counters.n * sizeof(unsigned int), s));
     {
-        const uint32_t warps_per_block = 8;
+        const uint32_t warps_per_block = 2;  // small CTAs: co-resident with the other lane's fill
         if(bt->raw) {
             // the counters buffer has one spare word: used as the "any ambiguity code" flag
             unsigned int* flag = bt->d_counters.p + bt->runs.size();
@@ -743,8 +788,10 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                   s>>>(bt->d_pairs.p, n, bt->d_anc.p, bt->d_des.p, bt->d_a.p, bt->d_b.p,
                                        bt->d_results.p, flag);
             unsigned int h_flag = 1;
+            trace_mark("  run: encode enqueued", n);
             CU_TRY(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
             CU_TRY(ctx, cudaStreamSynchronize(s));  // only this sub-batch's H2D + encode are waited on
+            trace_mark("  run: encode done", n);
             bt->nc = h_flag ? 16 : 4;
         } else
             validate_symbols_kernel<<<(n + warps_per_block - 1) / warps_per_block,
@@ -752,80 +799,109 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                                      bt->d_b.p, bt->d_results.p);
         ++bt->launches;
     }
-    if(bt->events.size() != 4 * bt->runs.size()) {
+    // events: 2 per run (fill start / end), then 5 per chunk (traceback start / end, expand start / end,
+    // inputs ready)
+    const size_t n_events = 2 * bt->runs.size() + 5 * bt->chunks.size();
+    cudaStream_t sf = bt->fill_stream ? bt->fill_stream : s;  // fills; fenced against s when distinct
+    if(bt->events.size() != n_events) {
         for(cudaEvent_t e : bt->events) cudaEventDestroy(e);
-        bt->events.assign(4 * bt->runs.size(), nullptr);
+        bt->events.assign(n_events, nullptr);
         for(cudaEvent_t& e : bt->events) CU_TRY(ctx, cudaEventCreate(&e));
     }
-    for(size_t ri = 0; ri < bt->runs.size(); ++ri) {
-        const Run& r = bt->runs[ri];
-        const uint32_t cnt = r.last - r.first;
-        cudaEvent_t* ev = &bt->events[4 * ri];
-        cudaEventRecord(ev[0], s);
-        if(r.cfg == 0) {
-            const uint32_t grid = std::min(cnt, bt->ring_ctas);
-            viterbi_generic_kernel<<<grid, 128, 0, s>>>(bt->d_pairs.p, r.first, r.last,
-                                                        bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                                                        ctx->d_table, ctx->gap, bt->d_ring.p,
-                                                        bt->ring_stride, bt->d_dirs.p,
-                                                        bt->d_results.p);
-            cudaEventRecord(ev[1], s);
-            traceback_kernel<DiagLayout, false><<<(cnt + 63) / 64, 64, 0, s>>>(
-                bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p,
-                bt->d_results.p);
-        } else {
-            const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg, bt->nc);
-            if(!pc) return COATI_GPU_E_ARG;
-            const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
-            if(pc->wave) {
-                const PairDesc& d = bt->descs[r.first];
-                const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
-                const uint32_t grid = std::min((nb + PIPE_WARPS - 1) / PIPE_WARPS, cap);
-                // NaN sentinel in every boundary entry: the data is its own ready flag
-                CU_TRY(ctx, cudaMemsetAsync(bt->d_bnd.p, 0xff,
-                                            (size_t)(nb + 1) * ((d.lb + 4) / 2) * sizeof(float4), s));
-                pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
-                    bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                    ctx->d_table, ctx->gap, bt->d_bnd.p, (d.lb + 4) / 2, bt->d_dirs.p,
-                    bt->d_results.p, bt->d_prog.p);
+    // Per chunk (one direction buffer): every fill first, then the tracebacks -- serial latency-bound
+    // walks, all in flight together -- then one expansion.  The small kernels are sized to fit beside
+    // the resident fill CTAs of the other pipeline lane (see traceback_chunk_kernel).
+    size_t ri = 0;
+    for(size_t ci = 0; ci < bt->chunks.size(); ++ci) {
+        const Chunk& ch = bt->chunks[ci];
+        const size_t ri0 = ri;
+        bool any_inter = false;
+        cudaEvent_t* cev = &bt->events[2 * bt->runs.size() + 5 * ci];
+        if(sf != s) {  // inputs / the direction buffer are ready: encode done, previous chunk walked
+            cudaEvent_t ready = cev[4];
+            if(ci == 0) cudaEventRecord(ready, s);
+            else ready = bt->events[2 * bt->runs.size() + 5 * (ci - 1) + 1];
+            CU_TRY(ctx, cudaStreamWaitEvent(sf, ready, 0));
+        }
+        for(; ri < bt->runs.size() && bt->runs[ri].chunk == ci; ++ri) {
+            const Run& r = bt->runs[ri];
+            const uint32_t cnt = r.last - r.first;
+            cudaEvent_t* ev = &bt->events[2 * ri];
+            cudaEventRecord(ev[0], sf);
+            if(r.cfg == 0) {
+                const uint32_t grid = std::min(cnt, bt->ring_ctas);
+                viterbi_generic_kernel<<<grid, 128, 0, sf>>>(bt->d_pairs.p, r.first, r.last,
+                                                            bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                                                            ctx->d_table, ctx->gap, bt->d_ring.p,
+                                                            bt->ring_stride, bt->d_dirs.p,
+                                                            bt->d_results.p);
+                any_inter = true;
             } else {
-                const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
-                const uint32_t grid = std::min(want, std::min(bt->bnd_ctas, cap));
-                if(pc->fn1)
-                    pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
+                const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg, bt->nc);
+                if(!pc) return COATI_GPU_E_ARG;
+                const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
+                if(pc->wave) {
+                    const PairDesc& d = bt->descs[r.first];
+                    const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
+                    const uint32_t grid = std::min((nb + PIPE_WARPS - 1) / PIPE_WARPS, cap);
+                    // NaN sentinel in every boundary entry: the data is its own ready flag
+                    CU_TRY(ctx, cudaMemsetAsync(bt->d_bnd.p, 0xff,
+                                                (size_t)(nb + 1) * ((d.lb + 4) / 2) * sizeof(float4), sf));
+                    pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
                         bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                        ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
-                        bt->d_results.p, nullptr);
-                else
-                    pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, s>>>(
-                        bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                        ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
-                        bt->d_results.p);
+                        ctx->d_table, ctx->gap, bt->d_bnd.p, (d.lb + 4) / 2, bt->d_dirs.p,
+                        bt->d_results.p, bt->d_prog.p);
+                } else {
+                    const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
+                    const uint32_t grid = std::min(want, std::min(bt->bnd_ctas, cap));
+                    if(pc->fn1)
+                        pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
+                            bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                            ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
+                            bt->d_results.p, nullptr);
+                    else
+                        pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
+                            bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                            ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
+                            bt->d_results.p);
+                    any_inter = true;
+                }
             }
-            cudaEventRecord(ev[1], s);
+            cudaEventRecord(ev[1], sf);
+            ++bt->launches;
+        }
+        if(sf != s && ri > ri0) CU_TRY(ctx, cudaStreamWaitEvent(s, bt->events[2 * (ri - 1) + 1], 0));
+        cudaEventRecord(cev[0], s);
+        for(size_t rj = ri0; rj < ri; ++rj) {  // long pairs: one warp per pair, with read-ahead
+            const Run& r = bt->runs[rj];
+            if(!(r.cfg & CFG_WAVE)) continue;
+            const uint32_t cnt = r.last - r.first;
 #define COATI_TB(RR)                                                                                   \
-    if(pc->wave)                                                                                       \
-        traceback_kernel<PipeLayoutR<RR>, true><<<cnt, 32, 0, s>>>(                                    \
-            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);   \
-    else                                                                                               \
-        traceback_kernel<PipeLayoutR<RR>, false><<<(cnt + 63) / 64, 64, 0, s>>>(                       \
-            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);
-            switch(pc->R) {
+    traceback_kernel<PipeLayoutR<RR>, true><<<cnt, 32, 0, s>>>(                                        \
+        bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);
+            switch(r.cfg & 0xffu) {
             case 2: COATI_TB(2) break;
-            case 3: COATI_TB(3) break;
             case 4: COATI_TB(4) break;
-            case 6: COATI_TB(6) break;
             case 8: COATI_TB(8) break;
             default: return COATI_GPU_E_ARG;
             }
 #undef COATI_TB
+            ++bt->launches;
         }
-        cudaEventRecord(ev[2], s);
-        expand_rows_kernel<<<(cnt + 7) / 8, 256, 0, s>>>(bt->d_pairs.p, r.first, r.last, bt->d_anc.p,
+        const uint32_t ccnt = ch.last - ch.first;
+        if(any_inter) {
+            traceback_chunk_kernel<<<(ccnt + 63) / 64, 64, 0, s>>>(bt->d_pairs.p, ch.first, ch.last,
+                                                                   bt->d_dirs.p, ctx->gap, bt->d_out_b.p,
+                                                                   bt->d_results.p);
+            ++bt->launches;
+        }
+        cudaEventRecord(cev[1], s);
+        cudaEventRecord(cev[2], s);
+        expand_rows_kernel<<<(ccnt + 1) / 2, 64, 0, s>>>(bt->d_pairs.p, ch.first, ch.last, bt->d_anc.p,
                                                          bt->d_des.p, bt->d_out_a.p, bt->d_out_b.p,
                                                          bt->d_results.p, ctx->gap.stop_gap);
-        cudaEventRecord(ev[3], s);
-        bt->launches += 3;
+        cudaEventRecord(cev[3], s);
+        ++bt->launches;
     }
     ctx->launches += bt->launches;
     CU_TRY(ctx, cudaGetLastError());
@@ -880,19 +956,25 @@ extern "C" int coati_gpu_batch_timing(coati_gpu_batch* bt, double* fill_ms, doub
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     CU_TRY(ctx, cudaStreamSynchronize(bt->stream));
     double f = 0, t = 0, c = 0;
-    for(size_t ri = 0; 4 * ri + 3 < bt->events.size(); ++ri) {
+    const size_t nr = bt->runs.size();
+    if(bt->events.size() == 2 * nr + 5 * bt->chunks.size()) {
         float ms = 0;
-        CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[4 * ri], bt->events[4 * ri + 1]));
-        f += ms;
-        CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[4 * ri + 1], bt->events[4 * ri + 2]));
-        t += ms;
-        CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[4 * ri + 2], bt->events[4 * ri + 3]));
-        c += ms;
+        for(size_t ri = 0; ri < nr; ++ri) {
+            CU_TRY(ctx, cudaEventElapsedTime(&ms, bt->events[2 * ri], bt->events[2 * ri + 1]));
+            f += ms;
+        }
+        for(size_t ci = 0; ci < bt->chunks.size(); ++ci) {
+            cudaEvent_t* cev = &bt->events[2 * nr + 5 * ci];
+            CU_TRY(ctx, cudaEventElapsedTime(&ms, cev[0], cev[1]));
+            t += ms;
+            CU_TRY(ctx, cudaEventElapsedTime(&ms, cev[2], cev[3]));
+            c += ms;
+        }
     }
     if(fill_ms) *fill_ms = f;
     if(traceback_ms) *traceback_ms = t;
     if(compact_ms) *compact_ms = c;
-    if(fill_launches) *fill_launches = bt->events.size() / 4;
+    if(fill_launches) *fill_launches = nr;
     return COATI_GPU_OK;
 }
 
@@ -915,26 +997,85 @@ extern "C" void coati_gpu_batch_destroy(coati_gpu_batch* bt) {
     delete bt;
 }
 
+// process_marginal's length checks (before trimming, utils.cc:819-837) and trim_end_stops
+// (utils.cc:945-967 via cod_int) for the raw pairs [p0, p1): bit 7 = bad length, bit 0 / 1 = the
+// ancestor / descendant ends with a stop codon.
+static void scan_raw_pairs(uint32_t k, const char* anc_all, const uint64_t* anc_off, const char* des_all,
+                           const uint64_t* des_off, size_t p0, size_t p1, uint8_t* raw) {
+    auto nuc = [](char ch) -> int {
+        switch(ch) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        default: return -1;
+        }
+    };
+    auto ends_with_stop = [&](const char* s, uint64_t len) {
+        if(len < 3) return false;
+        const int n0 = nuc(s[len - 3]), n1 = nuc(s[len - 2]), n2 = nuc(s[len - 1]);
+        if((n0 | n1 | n2) < 0) return false;
+        const int cod = (n0 << 4) | (n1 << 2) | n2;
+        return cod == 48 || cod == 50 || cod == 56;
+    };
+    for(size_t p = p0; p < p1; ++p) {
+        const uint64_t la = anc_off[p + 1] - anc_off[p], lb = des_off[p + 1] - des_off[p];
+        uint8_t f = 0;
+        if(la % 3 != 0 || la % k != 0 || lb % k != 0) f |= 0x80;
+        if(ends_with_stop(anc_all + anc_off[p], la)) f |= 1;
+        if(ends_with_stop(des_all + des_off[p], lb)) f |= 2;
+        raw[p] = f;
+    }
+}
+
 static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
                               const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
                               const char* anc_all, const char* des_all, char* out_a, char* out_b,
-                              uint64_t* out_len, float* score, int32_t* status, const uint8_t* raw,
+                              uint64_t* out_len, float* score, int32_t* status, bool raw_mode,
                               const uint32_t* model = nullptr) {
     if(!ctx || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
+    // raw pairs: the per-pair scan runs sub-batch by sub-batch, inside the pipeline
+    std::vector<uint8_t> rawbuf;
+    if(raw_mode) {
+        try {
+            rawbuf.resize(npairs);
+        } catch(const std::bad_alloc&) {
+            return COATI_GPU_E_NOMEM;
+        }
+    }
+    const uint8_t* raw = raw_mode ? rawbuf.data() : nullptr;
     // Large batches are cut into sub-batches that alternate between two streams, so that the host-side
     // planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its neighbours.
     const size_t kMinPipe = 32768;
     size_t nsub = 1;
-    if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(8, npairs / kMinPipe);
+    if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(16, npairs / kMinPipe);
     if(const char* env = std::getenv("COATI_GPU_NSUB")) nsub = std::max(1, std::atoi(env));  // tuning
     if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
-    coati_gpu_batch* bt[2] = {nullptr, nullptr};
-    size_t first[2] = {0, 0};
+    constexpr int NSLOT = 3;  // sub-batches in flight: one finishing, one filling, one queued behind it
+    coati_gpu_batch* bt[NSLOT] = {nullptr, nullptr, nullptr};
+    size_t first[NSLOT] = {0, 0, 0};
+    static_assert(NSLOT == coati_gpu_ctx::NLANE, "one lane per slot");
+    // direction-stream budget of a lane, from the memory free now (the GPU is idle: cheap call)
+    uint64_t lane_budget = 0;
+    if(nsub > 1) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->pool.idle_bytes();
+        const uint64_t sym = (a_off[npairs] - a_off[0]) + (b_off[npairs] - b_off[0]);
+        const uint64_t fixed_sub = (4 * sym + npairs * (2 + sizeof(PairDesc) + sizeof(PairResult))) / nsub * 5 / 4 +
+                                   (256ull << 20);
+        lane_budget = free_b > NSLOT * fixed_sub
+                          ? static_cast<uint64_t>((free_b - NSLOT * fixed_sub) * 0.85 / NSLOT) : (1ull << 20);
+    }
+    const bool trace = trace_on();
+    auto mark = [&](const char* what, size_t j) { trace_mark(what, j); };
     auto finish = [&](int slot) -> int {
         coati_gpu_batch* b = bt[slot];
         if(!b) return COATI_GPU_OK;
         bt[slot] = nullptr;
         int rc = COATI_GPU_OK;
+        mark("wait begin", first[slot]);
         if(cudaStreamSynchronize(b->stream) != cudaSuccess) {
             ctx->last_error = cudaGetErrorString(cudaGetLastError());
             rc = COATI_GPU_E_CUDA;
@@ -945,30 +1086,44 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
             if(score) score[first[slot] + p] = r.score;
             if(status) status[first[slot] + p] = r.status;
         }
+        if(trace && rc == COATI_GPU_OK) {
+            double fill = 0, tb = 0, ex = 0;
+            coati_gpu_batch_timing(b, &fill, &tb, &ex, nullptr);
+            std::fprintf(stderr, "[coati_gpu trace]              sub@%zu device ms: fill %.2f traceback %.2f expand %.2f\n",
+                         first[slot], fill, tb, ex);
+        }
+        mark("wait end", first[slot]);
         delete b;  // stream already drained
         return rc;
     };
     int rc = COATI_GPU_OK;
     for(size_t j = 0; j < nsub && rc == COATI_GPU_OK; ++j) {
-        const int slot = (int)(j & 1);
+        const int slot = (int)(j % NSLOT);
         rc = finish(slot);
         if(rc != COATI_GPU_OK) break;
         const size_t p0 = npairs * j / nsub, p1 = npairs * (j + 1) / nsub;
         first[slot] = p0;
-        rc = batch_create_on(ctx, slot ? ctx->stream2 : ctx->stream, nsub > 1 ? 0.5 : 1.0, p1 - p0,
+        mark("plan begin", p0);
+        if(raw_mode) scan_raw_pairs(ctx->gap.k, anc_all, a_off, des_all, b_off, p0, p1, rawbuf.data());
+        rc = batch_create_on(ctx, nsub > 1 ? ctx->lane_hi[slot] : ctx->stream,
+                             nsub > 1 ? ctx->lane_fill[slot] : ctx->stream, lane_budget, p1 - p0,
                              a_off + p0, b_off + p0, &bt[slot], raw ? raw + p0 : nullptr,
                              model ? model + p0 : nullptr);
         if(rc != COATI_GPU_OK) break;
+        mark("plan end", p0);
         const uint64_t ao = npairs ? a_off[p0] : 0, bo = npairs ? b_off[p0] : 0;
         rc = coati_gpu_batch_upload(bt[slot], a_all ? a_all + ao : nullptr, b_all ? b_all + bo : nullptr,
                                     anc_all ? anc_all + ao : nullptr, des_all ? des_all + bo : nullptr);
+        mark("upload enqueued", p0);
         if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt[slot]);
+        mark("run enqueued", p0);
         if(rc == COATI_GPU_OK)
             rc = batch_download_async(bt[slot], out_a ? out_a + ao + bo + p0 : nullptr,
                                       out_b ? out_b + ao + bo + p0 : nullptr);
+        mark("download enqueued", p0);
     }
-    for(int slot = 0; slot < 2; ++slot) {
-        const int r2 = finish(slot);
+    for(size_t j = nsub; j < nsub + NSLOT; ++j) {  // oldest first
+        const int r2 = finish((int)(j % NSLOT));
         if(rc == COATI_GPU_OK) rc = r2;
     }
     return rc;
@@ -980,7 +1135,7 @@ extern "C" int coati_gpu_viterbi_batch(coati_gpu_ctx* ctx, size_t npairs, const 
                                        const char* des_all, char* out_a, char* out_b,
                                        uint64_t* out_len, float* score, int32_t* status) {
     return viterbi_batch_impl(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
-                              out_len, score, status, nullptr);
+                              out_len, score, status, false);
 }
 
 // The leaf batch of the msa driver (align_msa.cc:285-318): every pair names its own substitution model
@@ -993,7 +1148,7 @@ extern "C" int coati_gpu_viterbi_batch_models(coati_gpu_ctx* ctx, size_t npairs,
                                               int32_t* status) {
     if(npairs && !model_idx) return COATI_GPU_E_ARG;
     return viterbi_batch_impl(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
-                              out_len, score, status, nullptr, model_idx);
+                              out_len, score, status, false, model_idx);
 }
 
 // marg_alignment (align_marginal.cc:44-88) for a batch of raw pairs: process_marginal's length checks
@@ -1005,39 +1160,8 @@ extern "C" int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, cons
                                          uint64_t* out_len, float* score, int32_t* status) {
     if(!ctx || (npairs && (!anc_off || !des_off || !anc_all || !des_all))) return COATI_GPU_E_ARG;
     if(!ctx->model_set) return COATI_GPU_E_ARG;
-    std::vector<uint8_t> raw;
-    try {
-        raw.assign(npairs, 0);
-    } catch(const std::bad_alloc&) {
-        return COATI_GPU_E_NOMEM;
-    }
-    const uint32_t k = ctx->gap.k;
-    auto nuc = [](char ch) -> int {
-        switch(ch) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': case 'U': case 'u': return 3;
-        default: return -1;
-        }
-    };
-    auto ends_with_stop = [&](const char* s, uint64_t len) {  // utils.cc:945-967 via cod_int
-        if(len < 3) return false;
-        const int n0 = nuc(s[len - 3]), n1 = nuc(s[len - 2]), n2 = nuc(s[len - 1]);
-        if((n0 | n1 | n2) < 0) return false;
-        const int cod = (n0 << 4) | (n1 << 2) | n2;
-        return cod == 48 || cod == 50 || cod == 56;
-    };
-    for(size_t p = 0; p < npairs; ++p) {
-        const uint64_t la = anc_off[p + 1] - anc_off[p], lb = des_off[p + 1] - des_off[p];
-        uint8_t f = 0;
-        if(la % 3 != 0 || la % k != 0 || lb % k != 0) f |= 0x80;
-        if(ends_with_stop(anc_all + anc_off[p], la)) f |= 1;
-        if(ends_with_stop(des_all + des_off[p], lb)) f |= 2;
-        raw[p] = f;
-    }
     return viterbi_batch_impl(ctx, npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b,
-                              out_len, score, status, raw.data());
+                              out_len, score, status, true);
 }
 
 extern "C" int coati_gpu_viterbi(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,

@@ -97,17 +97,11 @@ struct PipeLayout {
 // it records one op byte per alignment column (0 = M, 1 = D, 2 = I), right-aligned in the pair's
 // out_b slot; expand_rows_kernel then builds both rows in parallel with coalesced accesses.
 template <class Layout, bool WARP>
-__global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
-                                 const uint8_t* __restrict__ dirs, GapConsts gap,
-                                 char* __restrict__ out_b, PairResult* __restrict__ results) {
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t p = first + (WARP ? gtid >> 5 : gtid);
+__device__ __forceinline__ void traceback_walk(const PairDesc& pd, const uint8_t* __restrict__ dirs,
+                                               const GapConsts& gap, char* __restrict__ out_b,
+                                               PairResult& res) {
     const uint32_t lane = WARP ? (threadIdx.x & 31) : 0;
     const bool lead = lane == 0;
-    if(p >= last) return;
-    const PairDesc pd = pairs[p];
-    PairResult& res = results[pd.orig];
-    if(res.status != 0) return;
     const uint32_t la = pd.la, lb = pd.lb, k = gap.k;
     const uint8_t* dir = dirs + pd.dir_off;
     char* ops = out_b + pd.out_off;
@@ -203,13 +197,55 @@ __global__ void traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t fi
     res.start = pos;
 }
 
+template <class Layout, bool WARP>
+__global__ void __launch_bounds__(64)
+traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+                 const uint8_t* __restrict__ dirs, GapConsts gap, char* __restrict__ out_b,
+                 PairResult* __restrict__ results) {
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = first + (WARP ? gtid >> 5 : gtid);
+    if(p >= last) return;
+    const PairDesc pd = pairs[p];
+    PairResult& res = results[pd.orig];
+    if(res.status != 0) return;
+    traceback_walk<Layout, WARP>(pd, dirs, gap, out_b, res);
+}
+
+// One thread per pair over a whole chunk of inter-pair runs: the layout follows the pair's own kernel
+// configuration (rows per lane R, or 0 for the anti-diagonal layout of the generic kernel), so all the
+// walks of a chunk -- each a serial, latency-bound chain -- are in flight together instead of one
+// launch per configuration.  Pairs are sorted by configuration, so a warp rarely mixes two layouts.
+// 64 threads x 32 registers: small enough to be co-resident with the fill CTAs of the next sub-batch.
+__global__ void __launch_bounds__(64, 32)
+traceback_chunk_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+                       const uint8_t* __restrict__ dirs, GapConsts gap, char* __restrict__ out_b,
+                       PairResult* __restrict__ results) {
+    const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= last) return;
+    const PairDesc pd = pairs[p];
+    if(pd.cfg & CFG_WAVE) return;  // long pairs: warp-per-pair launch with read-ahead
+    PairResult& res = results[pd.orig];
+    if(res.status != 0) return;
+    switch(pd.cfg & 0xffu) {
+    case 0: traceback_walk<DiagLayout, false>(pd, dirs, gap, out_b, res); break;
+    case 2: traceback_walk<PipeLayoutR<2>, false>(pd, dirs, gap, out_b, res); break;
+    case 3: traceback_walk<PipeLayoutR<3>, false>(pd, dirs, gap, out_b, res); break;
+    case 4: traceback_walk<PipeLayoutR<4>, false>(pd, dirs, gap, out_b, res); break;
+    case 6: traceback_walk<PipeLayoutR<6>, false>(pd, dirs, gap, out_b, res); break;
+    case 8: traceback_walk<PipeLayoutR<8>, false>(pd, dirs, gap, out_b, res); break;
+    default: res.status = -8; res.len = 0; res.start = pd.la + pd.lb; break;
+    }
+}
+
 // One warp per pair: expand the op bytes (right-aligned in the out_b slot, first op at res.start)
 // into the two gapped rows, left-aligned and NUL-terminated (align_pair.cc:270-302: MATCH emits
 // (anc, des), DELETION (anc, '-'), INSERTION ('-', des); the reference reverses at the end, here the
 // ops are simply read front to back).  Source indices are running counts of the ops seen so far
 // (warp ballot + popcount).  In-place on out_b is safe: chunk i is read before chunk i is written and
 // reads never trail writes (read index = write index + start).
-__global__ void expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+// (64 threads x 32 registers per CTA, see traceback_chunk_kernel)
+__global__ void __launch_bounds__(64, 32)
+expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                                    const char* __restrict__ anc_all, const char* __restrict__ des_all,
                                    char* __restrict__ out_a, char* __restrict__ out_b,
                                    PairResult* __restrict__ results, float stop_gap) {
