@@ -225,7 +225,7 @@ PipeCfg make_cfg() {
 }
 template <int R, bool WAVE, int NC>
 PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false) or intra-pair wavefront
-    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, nullptr, viterbi_pipe1_kernel<R, WAVE, NC>,
+    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, nullptr, viterbi_pipe1_kernel<R, WAVE, NC, true>,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
 }
 template <int R, int NC>
@@ -353,6 +353,16 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
             g_pipe_cfgs[3].fn = viterbi_pipe_kernel<3, 6>, g_pipe_cfgs[3].fn1 = nullptr;
             g_pipe_cfgs[3].smem = (size_t)PIPE_WARPS * 2 * 16 * 32 * sizeof(float4);
             g_pipe_cfgs[10].k = 0;  // disable the ACGT-only K = 3 variant as well
+        }
+    }
+    if(const char* env = std::getenv("COATI_GPU_PIPE_SGN")) {  // A/B: FSETP + IMAD decisions for K = 1
+        if(env[0] == '0') {
+            g_pipe_cfgs[0].fn1 = viterbi_pipe1_kernel<4, false, 16, false>;
+            g_pipe_cfgs[1].fn1 = viterbi_pipe1_kernel<8, false, 16, false>;
+            g_pipe_cfgs[7].fn1 = viterbi_pipe1_kernel<4, false, 4, false>;
+            g_pipe_cfgs[8].fn1 = viterbi_pipe1_kernel<8, false, 4, false>;
+            g_pipe_cfgs[5].fn1 = viterbi_pipe1_kernel<4, true, 16, false>;
+            g_pipe_cfgs[6].fn1 = viterbi_pipe1_kernel<8, true, 16, false>;
         }
     }
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';

@@ -38,6 +38,16 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {  // two independent round-to-ne
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
     return r;
 }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+// acc = (acc << 1) | sign(d): one funnel shift.  For finite a <= b, sign(a - b) is set exactly when
+// a != b (a - a is +0 in round-to-nearest), and sign(a - b) is set exactly when b > a.
+__device__ __forceinline__ void push_sign(uint32_t& acc, float d) {
+    acc = __funnelshift_l(__float_as_uint(d), acc, 1);
+}
 
 // acc |= bm when a == b / a > b, as FSETP + predicated LOP3 (the compiler's own lowering of
 // `if(a == b) acc |= bm` is FSETP + SEL + LOP3)
@@ -67,6 +77,36 @@ __device__ __forceinline__ void or_if_gt(uint32_t& acc, float a, float b, uint32
         D = Y;                                                                               \
     }
 
+// Sign-shift form of a row PAIR (SGN kernels): the five decisions of both rows are the sign bits of
+// five packed subtractions, pushed into the plane accumulators by funnel shifts -- 1.5 instructions per
+// decision bit instead of FSETP + predicated IMAD.  Planes 0-3 are accumulated inverted (bit = "differs
+// from the maximum") and complemented at the flush.  Every score is finite here (|x| <= FLT_MAX and the
+// penalties cannot round LOWEST away from -FLT_MAX), so the differences never produce NaN or -0.
+#define COATI_ROWPAIR_SGN(q)                                                                  \
+    {                                                                                         \
+        const f2 M2 = mk2(Mv[q], Mv[q + 1]);                                                  \
+        const f2 I2 = mk2(Zp[q], Zp[q + 1]);                                                  \
+        const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2); \
+        const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2); \
+        const float xd0 = D + g.gs, yd0 = D + g.ge;                                           \
+        const float X0 = fmaxf(fmaxf(lo2(xm), xd0), lo2(xi));                                 \
+        const float Y0 = fmaxf(fmaxf(lo2(ym), yd0), lo2(yi));                                 \
+        const float xd1 = Y0 + g.gs, yd1 = Y0 + g.ge;                                         \
+        const float X1 = fmaxf(fmaxf(hi2(xm), xd1), hi2(xi));                                 \
+        const float Y1 = fmaxf(fmaxf(hi2(ym), yd1), hi2(yi));                                 \
+        D = Y1;                                                                               \
+        const f2 X2 = mk2(X0, X1), Y2 = mk2(Y0, Y1);                                          \
+        const f2 d0 = sub2(xm, X2), d1 = sub2(mk2(xd0, xd1), X2);                             \
+        const f2 d2 = sub2(ym, Y2), d3 = sub2(mk2(yd0, yd1), Y2), d4 = sub2(zi, zm);          \
+        push_sign(acc[q][0], lo2(d0)), push_sign(acc[q + 1][0], hi2(d0));                     \
+        push_sign(acc[q][1], lo2(d1)), push_sign(acc[q + 1][1], hi2(d1));                     \
+        push_sign(acc[q][2], lo2(d2)), push_sign(acc[q + 1][2], hi2(d2));                     \
+        push_sign(acc[q][3], lo2(d3)), push_sign(acc[q + 1][3], hi2(d3));                     \
+        push_sign(acc[q][4], lo2(d4)), push_sign(acc[q + 1][4], hi2(d4));                     \
+        Xp[q] = X0, Xp[q + 1] = X1;                                                           \
+        Zp[q] = fmaxf(lo2(zm), lo2(zi)), Zp[q + 1] = fmaxf(hi2(zm), hi2(zi));                 \
+    }
+
 // WAVE = false: inter-pair scheme, one warp per pair, bands of a pair processed one after another by
 //                the same warp (pairs [first, last) pulled from `counter`).
 // WAVE = true : intra-pair scheme for long pairs: the kernel works on the single pair `first`; every
@@ -88,7 +128,8 @@ constexpr uint32_t WAVE_BLOCK = 32;  // columns of the row above fetched per ref
 // NC = substitution-table columns kept per lane: 16 (all IUPAC codes) or 4 when no descendant of the
 // batch carries an ambiguity code (the common case) -- a quarter of the shared memory, so more
 // resident warps to fill issue slots.
-template <int R, bool WAVE, int NC>
+// SGN = decisions by sign-shift (COATI_ROWPAIR_SGN) instead of FSETP + predicated IMAD.
+template <int R, bool WAVE, int NC, bool SGN = false>
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
@@ -241,8 +282,18 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                         sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
                     }
                     float D = recvY, dXq = diagX;
+                    float Mv[R];  // SGN: every match score first, from the previous column's X
+                    if(SGN) {
+                        Mv[0] = diagX + sv[0];
+#pragma unroll
+                        for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
+                    }
 #pragma unroll
                     for(int q = 0; q < R; q += 2) {
+                        if(SGN) {
+                            COATI_ROWPAIR_SGN(q)
+                            continue;
+                        }
                         const f2 M2 = add2(mk2(dXq, Xp[q]), mk2(sv[q], sv[q + 1]));
                         const f2 I2 = mk2(Zp[q], Zp[q + 1]);
                         const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2);
@@ -267,6 +318,14 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     uint32_t w[WPL];
 #pragma unroll
                     for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
+                    if(SGN) {
+                        // bits were pushed in at the bottom: the lane's last column of this block goes
+                        // to bit 31 - step % 32 (a lane that ends inside the block stopped pushing early)
+                        const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
+                        const uint32_t sh = 31u - (t_end & 31u);
+#pragma unroll
+                        for(int x = 0; x < 5 * R; ++x) w[x] = (x % 5 < 4 ? ~w[x] : w[x]) << sh;
+                    }
 #pragma unroll
                     for(int x = 0; x < (int)WPL / 4; ++x)
                         dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
@@ -294,5 +353,6 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
 }
 
 #undef COATI_ROW
+#undef COATI_ROWPAIR_SGN
 
 }  // namespace coati_gpu

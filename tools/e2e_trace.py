@@ -1,6 +1,7 @@
 """One traced call of coati_gpu_alignpair_batch on the C5 workload (COATI_GPU_TRACE timeline on stderr)."""
 import os, sys, time
-os.environ["COATI_GPU_TRACE"] = "1"  # read once by the library
+if os.environ.get("TRACE", "1") == "1":
+    os.environ["COATI_GPU_TRACE"] = "1"  # read once by the library
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, coati_b200
 from coati_b200 import capi
@@ -28,6 +29,6 @@ print("e2e ms %.1f GCUPS %.0f" % (1e3 * (t1 - t0), cells / (t1 - t0) / 1e9), flu
 for nsub in sys.argv[1:]:
     os.environ["COATI_GPU_NSUB"] = nsub
     ts = []
-    for _ in range(3):
+    for _ in range(int(os.environ.get("REPS", 3))):
         t0 = time.perf_counter(); once(); ts.append(time.perf_counter() - t0)
     print("nsub", nsub, "e2e ms", [round(1e3 * t, 1) for t in ts], "GCUPS %.0f" % (cells / min(ts) / 1e9), flush=True)
