@@ -310,10 +310,11 @@ def main():
             score.ctypes.data_as(coati_b200.capi._fp), status.ctypes.data_as(coati_b200.capi._i32p)))
 
     batch.destroy()
-    e2e_once()                                  # warm-up (allocations, page faults)
+    for _ in range(max(1, args.warmup)):         # warm-up (pool allocations, page faults)
+        e2e_once()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     for _ in range(e2e_steps):
         e2e_once()
     torch.cuda.synchronize()

@@ -39,9 +39,12 @@ static void trace_mark(const char* what, size_t id) {
     std::fprintf(stderr, "[coati_gpu trace] %9.2f ms  %-22s %zu\n", ms, what, id);
 }
 
+
 // ---------------------------------------------------------------------------------------------
 // Grow-only device memory pool: batches borrow blocks and give them back, so repeated calls of the
 // public batch entry point do not pay cudaMalloc/cudaFree (which synchronise the device).
+static uint64_t g_alloc_epoch = 0;  // bumped by every device allocation / free made outside the pool
+
 struct DevPool {
     struct Block {
         void* p;
@@ -49,25 +52,36 @@ struct DevPool {
         bool used;
     };
     std::vector<Block> blocks;
+    uint64_t generation = 0;  // bumped by every cudaMalloc / cudaFree of the pool
     void* take(size_t bytes, cudaError_t* err) {
         *err = cudaSuccess;
         if(bytes == 0) return nullptr;
         Block* best = nullptr;
         for(Block& b : blocks)
             if(!b.used && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
-        if(best && best->bytes <= 2 * bytes + (1u << 20)) {
+        if(best && best->bytes <= 2 * bytes + (4u << 20)) {
             best->used = true;
             return best->p;
         }
+        // new block: some headroom, so the slightly larger sibling sub-batches of a pipelined call
+        // find it big enough (cudaMalloc synchronises the device: a miss stalls the pipeline)
         void* p = nullptr;
-        *err = cudaMalloc(&p, bytes);
+        trace_mark("    pool miss (MiB)", bytes >> 20);
+        size_t padded = (bytes + bytes / 8 + 511) & ~size_t(511);
+        *err = cudaMalloc(&p, padded);
+        if(*err != cudaSuccess) {
+            cudaGetLastError();
+            padded = bytes;
+            *err = cudaMalloc(&p, padded);
+        }
         if(*err != cudaSuccess) {  // release idle blocks and retry once
             cudaGetLastError();
             trim();
-            *err = cudaMalloc(&p, bytes);
+            *err = cudaMalloc(&p, padded);
             if(*err != cudaSuccess) return nullptr;
         }
-        blocks.push_back(Block{p, bytes, true});
+        blocks.push_back(Block{p, padded, true});
+        ++generation;
         return p;
     }
     void give(void* p) {
@@ -75,6 +89,7 @@ struct DevPool {
             if(b.p == p) b.used = false;
     }
     void trim() {
+        ++generation;
         for(size_t i = 0; i < blocks.size();) {
             if(!blocks[i].used) {
                 cudaFree(blocks[i].p);
@@ -111,11 +126,12 @@ struct HostPool {
             return best->p;
         }
         void* p = nullptr;
-        if(cudaMallocHost(&p, bytes) != cudaSuccess) {
+        const size_t padded = (bytes + bytes / 8 + 4095) & ~size_t(4095);
+        if(cudaMallocHost(&p, padded) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }
-        blocks.push_back(Block{p, bytes, true});
+        blocks.push_back(Block{p, padded, true});
         return p;
     }
     void give(void* p) {
@@ -148,6 +164,20 @@ struct coati_gpu_ctx {
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
     DevPool pool;
     HostPool hpool;
+    // cudaMemGetInfo costs tens of ms on a device with a lot of memory mapped: ask again only when the
+    // pool has allocated or freed since the last answer
+    size_t cached_free = 0;
+    uint64_t cached_free_gen = ~0ull;
+    cudaError_t free_bytes(size_t* out) {
+        if(cached_free_gen != pool.generation + g_alloc_epoch) {
+            size_t total_b = 0;
+            cudaError_t e = cudaMemGetInfo(&cached_free, &total_b);
+            if(e != cudaSuccess) return e;
+            cached_free_gen = pool.generation + g_alloc_epoch;
+        }
+        *out = cached_free;
+        return cudaSuccess;
+    }
 };
 
 #define CU_TRY(ctx, expr)                                                                   \
@@ -177,12 +207,16 @@ struct DevBuf {
             p = static_cast<T*>(pool->take(count * sizeof(T), &e));
             return e;
         }
+        ++g_alloc_epoch;
         return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
     }
     void release() {
         if(p) {
             if(pool) pool->give(p);
-            else cudaFree(p);
+            else {
+                cudaFree(p);
+                ++g_alloc_epoch;
+            }
         }
         p = nullptr;
         n = 0;
@@ -230,7 +264,7 @@ PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false)
 }
 template <int R, int NC>
 PipeCfg make_cfg3() {  // K = 3: FADD2 specialisation (viterbi_pipe3.cuh)
-    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, nullptr, viterbi_pipe3_kernel<R, NC>,
+    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, nullptr, viterbi_pipe3_kernel<R, NC, true>,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
 }
 PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false, 16>(), make_cfg1<8, false, 16>(), make_cfg<3, 3>(),
@@ -361,6 +395,8 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
             g_pipe_cfgs[1].fn1 = viterbi_pipe1_kernel<8, false, 16, false>;
             g_pipe_cfgs[7].fn1 = viterbi_pipe1_kernel<4, false, 4, false>;
             g_pipe_cfgs[8].fn1 = viterbi_pipe1_kernel<8, false, 4, false>;
+            g_pipe_cfgs[3].fn1 = viterbi_pipe3_kernel<6, 16, false>;
+            g_pipe_cfgs[10].fn1 = viterbi_pipe3_kernel<6, 4, false>;
             g_pipe_cfgs[5].fn1 = viterbi_pipe1_kernel<4, true, 16, false>;
             g_pipe_cfgs[6].fn1 = viterbi_pipe1_kernel<8, true, 16, false>;
         }
@@ -608,8 +644,8 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
     trace_mark("  plan: sorted", npairs);
     uint64_t budget = ctx->dir_budget ? ctx->dir_budget : lane_budget;
     if(budget == 0) {  // (cudaMemGetInfo can block for tens of ms while kernels run: never inside the pipeline)
-        size_t free_b = 0, total_b = 0;
-        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        size_t free_b = 0;
+        CU_TRY(ctx, ctx->free_bytes(&free_b));
         free_b += ctx->pool.idle_bytes();
         const uint64_t fixed = 2 * (bt->a_total + bt->b_total) + 2 * bt->out_total +
                                npairs * (sizeof(PairDesc) + sizeof(PairResult)) + (256ull << 20);
@@ -1068,9 +1104,9 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
     // direction-stream budget of a lane, from the memory free now (the GPU is idle: cheap call)
     uint64_t lane_budget = 0;
     if(nsub > 1) {
-        size_t free_b = 0, total_b = 0;
+        size_t free_b = 0;
         CU_TRY(ctx, cudaSetDevice(ctx->device));
-        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        CU_TRY(ctx, ctx->free_bytes(&free_b));
         free_b += ctx->pool.idle_bytes();
         const uint64_t sym = (a_off[npairs] - a_off[0]) + (b_off[npairs] - b_off[0]);
         const uint64_t fixed_sub = (4 * sym + npairs * (2 + sizeof(PairDesc) + sizeof(PairResult))) / nsub * 5 / 4 +

@@ -34,7 +34,41 @@ namespace coati_gpu {
         Zh[q][0] = fmaxf(zmkq, ikq);                                                         \
     }
 
-template <int R, int NC>
+// Sign-shift form of a row pair (see COATI_ROWPAIR_SGN in viterbi_pipe1.cuh): decisions are the sign
+// bits of packed subtractions against the decision maxima X and Yd.
+#define COATI_ROWPAIR3_SGN(q)                                                                 \
+    {                                                                                         \
+        const f2 M2 = mk2(Mv[q], Mv[q + 1]);                                                  \
+        const f2 I2 = mk2(Zh[q][K - 1], Zh[q + 1][K - 1]);                                    \
+        const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2); \
+        const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2); \
+        const f2 zmk = add2(zm, gk12), ik = add2(I2, gk2);                                    \
+        const float D0 = (q) < 3 ? recvY[(q) < 3 ? (q) : 0] : Ycur[(q) >= 3 ? (q)-3 : 0];     \
+        const float D1 = (q) + 1 < 3 ? recvY[(q) + 1 < 3 ? (q) + 1 : 0] : Ycur[(q) + 1 >= 3 ? (q)-2 : 0]; \
+        const f2 Dp = mk2(D0, D1);                                                            \
+        const f2 xd = add2(Dp, gs2), yd = add2(Dp, ge2), dk = add2(Dp, gk2);                  \
+        const float X0 = fmaxf(fmaxf(lo2(xm), lo2(xd)), lo2(xi));                             \
+        const float X1 = fmaxf(fmaxf(hi2(xm), hi2(xd)), hi2(xi));                             \
+        const float Y0 = fmaxf(fmaxf(lo2(ym), lo2(yd)), lo2(yi));                             \
+        const float Y1 = fmaxf(fmaxf(hi2(ym), hi2(yd)), hi2(yi));                             \
+        const f2 X2 = mk2(X0, X1), Y2 = mk2(Y0, Y1);                                          \
+        const f2 d0 = sub2(xm, X2), d1 = sub2(xd, X2), d2 = sub2(ym, Y2), d3 = sub2(yd, Y2);  \
+        const f2 d4 = sub2(zi, zm);                                                           \
+        push_sign(acc[q][0], lo2(d0)), push_sign(acc[q + 1][0], hi2(d0));                     \
+        push_sign(acc[q][1], lo2(d1)), push_sign(acc[q + 1][1], hi2(d1));                     \
+        push_sign(acc[q][2], lo2(d2)), push_sign(acc[q + 1][2], hi2(d2));                     \
+        push_sign(acc[q][3], lo2(d3)), push_sign(acc[q + 1][3], hi2(d3));                     \
+        push_sign(acc[q][4], lo2(d4)), push_sign(acc[q + 1][4], hi2(d4));                     \
+        Xp[q] = X0, Xp[q + 1] = X1;                                                           \
+        /* fill maxima (align_pair.cc:106-118): max(max(ym, yi) + gk1, D + gk) */             \
+        const f2 ymi = add2(mk2(fmaxf(lo2(ym), lo2(yi)), fmaxf(hi2(ym), hi2(yi))), gk12);     \
+        Ycur[q] = fmaxf(lo2(ymi), lo2(dk)), Ycur[q + 1] = fmaxf(hi2(ymi), hi2(dk));           \
+        Zh[q][2] = Zh[q][1], Zh[q + 1][2] = Zh[q + 1][1];                                     \
+        Zh[q][1] = Zh[q][0], Zh[q + 1][1] = Zh[q + 1][0];                                     \
+        Zh[q][0] = fmaxf(lo2(zmk), lo2(ik)), Zh[q + 1][0] = fmaxf(hi2(zmk), hi2(ik));         \
+    }
+
+template <int R, int NC, bool SGN = false>
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
@@ -139,6 +173,16 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                         sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
                     }
                     float dXq = diagX;
+                    if(SGN) {
+                        // every match score first, from the previous column's X; D of a row is this
+                        // column's Y three rows up (rows are evaluated top down)
+                        float Mv[R];
+                        Mv[0] = diagX + sv[0];
+#pragma unroll
+                        for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
+#pragma unroll
+                        for(int q = 0; q < R; q += 2) COATI_ROWPAIR3_SGN(q)
+                    } else
 #pragma unroll
                     for(int q = 0; q < R; q += 2) {
                         const f2 M2 = add2(mk2(dXq, Xp[q]), mk2(sv[q], sv[q + 1]));
@@ -165,6 +209,12 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     uint32_t w[WPL];
 #pragma unroll
                     for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
+                    if(SGN) {  // see viterbi_pipe1.cuh: align the pushed bits, complement planes 0-3
+                        const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
+                        const uint32_t sh = 31u - (t_end & 31u);
+#pragma unroll
+                        for(int x = 0; x < 5 * R; ++x) w[x] = (x % 5 < 4 ? ~w[x] : w[x]) << sh;
+                    }
 #pragma unroll
                     for(int x = 0; x < (int)WPL / 4; ++x)
                         dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
@@ -190,5 +240,6 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
 }
 
 #undef COATI_ROW3
+#undef COATI_ROWPAIR3_SGN
 
 }  // namespace coati_gpu
