@@ -264,7 +264,7 @@ PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false)
 }
 template <int R, int NC>
 PipeCfg make_cfg3() {  // K = 3: FADD2 specialisation (viterbi_pipe3.cuh)
-    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, nullptr, viterbi_pipe3_kernel<R, NC, true>,
+    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, nullptr, viterbi_pipe3_kernel<R, NC>,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
 }
 PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false, 16>(), make_cfg1<8, false, 16>(), make_cfg<3, 3>(),
@@ -395,8 +395,6 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
             g_pipe_cfgs[1].fn1 = viterbi_pipe1_kernel<8, false, 16, false>;
             g_pipe_cfgs[7].fn1 = viterbi_pipe1_kernel<4, false, 4, false>;
             g_pipe_cfgs[8].fn1 = viterbi_pipe1_kernel<8, false, 4, false>;
-            g_pipe_cfgs[3].fn1 = viterbi_pipe3_kernel<6, 16, false>;
-            g_pipe_cfgs[10].fn1 = viterbi_pipe3_kernel<6, 4, false>;
             g_pipe_cfgs[5].fn1 = viterbi_pipe1_kernel<4, true, 16, false>;
             g_pipe_cfgs[6].fn1 = viterbi_pipe1_kernel<8, true, 16, false>;
         }

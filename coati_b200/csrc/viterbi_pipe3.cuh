@@ -10,36 +10,20 @@
 //   (align_pair.cc:285-296), so the decision maxima and the fill maxima are separate.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "viterbi_pipe.cuh"
 #include "viterbi_pipe1.cuh"
 
 namespace coati_gpu {
 
-#define COATI_ROW3(q, xmq, ymq, zmq, xiq, yiq, ziq, zmkq, ikq)                                \
-    {                                                                                        \
-        const float D = (q) < 3 ? recvY[(q) < 3 ? (q) : 0] : Ycur[(q) >= 3 ? (q)-3 : 0];     \
-        const float xd = D + g.gs, yd = D + g.ge;                                            \
-        const float X = fmaxf(fmaxf(xmq, xd), xiq);                                          \
-        const float Yd = fmaxf(fmaxf(ymq, yd), yiq);                                         \
-        or_if_eq(acc[q][0], xmq, X, bm, one);                                                \
-        or_if_eq(acc[q][1], xd, X, bm, one);                                                 \
-        or_if_eq(acc[q][2], ymq, Yd, bm, one);                                               \
-        or_if_eq(acc[q][3], yd, Yd, bm, one);                                                \
-        or_if_gt(acc[q][4], zmq, ziq, bm, one);                                              \
-        Xp[q] = X;                                                                           \
-        Ycur[q] = fmaxf(fmaxf(ymq, yiq) + g.gk1, D + g.gk);                                  \
-        Zh[q][2] = Zh[q][1];                                                                 \
-        Zh[q][1] = Zh[q][0];                                                                 \
-        Zh[q][0] = fmaxf(zmkq, ikq);                                                         \
-    }
-
 // Sign-shift form of a row pair (see COATI_ROWPAIR_SGN in viterbi_pipe1.cuh): decisions are the sign
 // bits of packed subtractions against the decision maxima X and Yd.
-#define COATI_ROWPAIR3_SGN(q)                                                                 \
+#define COATI_ROWPAIR3_SGN(q, ZS)                                                               \
     {                                                                                         \
         const f2 M2 = mk2(Mv[q], Mv[q + 1]);                                                  \
-        const f2 I2 = mk2(Zh[q][K - 1], Zh[q + 1][K - 1]);                                    \
+        const f2 I2 = mk2(Zh[q][ZS], Zh[q + 1][ZS]); /* Z of three columns back */            \
         const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2); \
         const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2); \
         const f2 zmk = add2(zm, gk12), ik = add2(I2, gk2);                                    \
@@ -63,12 +47,10 @@ namespace coati_gpu {
         /* fill maxima (align_pair.cc:106-118): max(max(ym, yi) + gk1, D + gk) */             \
         const f2 ymi = add2(mk2(fmaxf(lo2(ym), lo2(yi)), fmaxf(hi2(ym), hi2(yi))), gk12);     \
         Ycur[q] = fmaxf(lo2(ymi), lo2(dk)), Ycur[q + 1] = fmaxf(hi2(ymi), hi2(dk));           \
-        Zh[q][2] = Zh[q][1], Zh[q + 1][2] = Zh[q + 1][1];                                     \
-        Zh[q][1] = Zh[q][0], Zh[q + 1][1] = Zh[q + 1][0];                                     \
-        Zh[q][0] = fmaxf(lo2(zmk), lo2(ik)), Zh[q + 1][0] = fmaxf(hi2(zmk), hi2(ik));         \
+        Zh[q][ZS] = fmaxf(lo2(zmk), lo2(ik)), Zh[q + 1][ZS] = fmaxf(hi2(zmk), hi2(ik));       \
     }
 
-template <int R, int NC, bool SGN = false>
+template <int R, int NC>
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
@@ -89,7 +71,6 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     const f2 ng2 = mk2(g.ng, g.ng), go2 = mk2(g.go, g.go), gs2 = mk2(g.gs, g.gs), ge2 = mk2(g.ge, g.ge);
     const f2 gk12 = mk2(g.gk1, g.gk1), gk2 = mk2(g.gk, g.gk);
     const char* tab_lane = reinterpret_cast<const char*>(s_tab) + lane * 16;
-    const uint32_t one = g.k / 3;  // == 1, opaque to the compiler (keeps the accumulate an IMAD)
 
     for(;;) {
         uint32_t p = 0;
@@ -155,7 +136,10 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             uint32_t u = 0u - (uint32_t)lane;
             __syncwarp();
 
-            for(uint32_t t = 0; t < nsteps; ++t, ++u) {
+            // Z(r, c) is read three columns later: the history is a ring indexed by step % 3 (a lane's
+            // steps are consecutive), fixed at compile time by unrolling the step loop three times
+            auto step = [&](auto zs_c, const uint32_t t) {
+                constexpr int ZS = decltype(zs_c)::value;
                 const float recvX = __shfl_sync(FULL, outX, rot);
                 recvY[0] = __shfl_sync(FULL, outY0, rot);
                 recvY[1] = __shfl_sync(FULL, outY1, rot);
@@ -165,35 +149,20 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                 const float4 bnv = bin[cn];
                 const uint32_t bl = b[cn - 1];
                 if(u < lb) {
-                    const uint32_t bm = 1u << (31 - (t & 31));
                     float sv[R4 * 4];
 #pragma unroll
                     for(int h = 0; h < R4; ++h) {
                         const float4 v = *reinterpret_cast<const float4*>(tab_lane + bo + h * (NC * 512));
                         sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
                     }
-                    float dXq = diagX;
-                    if(SGN) {
-                        // every match score first, from the previous column's X; D of a row is this
-                        // column's Y three rows up (rows are evaluated top down)
-                        float Mv[R];
-                        Mv[0] = diagX + sv[0];
+                    // every match score first, from the previous column's X; D of a row is this
+                    // column's Y three rows up (rows are evaluated top down)
+                    float Mv[R];
+                    Mv[0] = diagX + sv[0];
 #pragma unroll
-                        for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
+                    for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
 #pragma unroll
-                        for(int q = 0; q < R; q += 2) COATI_ROWPAIR3_SGN(q)
-                    } else
-#pragma unroll
-                    for(int q = 0; q < R; q += 2) {
-                        const f2 M2 = add2(mk2(dXq, Xp[q]), mk2(sv[q], sv[q + 1]));
-                        const f2 I2 = mk2(Zh[q][K - 1], Zh[q + 1][K - 1]);
-                        const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2);
-                        const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2);
-                        const f2 zmk = add2(zm, gk12), ik = add2(I2, gk2);  // fill terms (:106-118)
-                        dXq = Xp[q + 1];
-                        COATI_ROW3(q, lo2(xm), lo2(ym), lo2(zm), lo2(xi), lo2(yi), lo2(zi), lo2(zmk), lo2(ik))
-                        COATI_ROW3(q + 1, hi2(xm), hi2(ym), hi2(zm), hi2(xi), hi2(yi), hi2(zi), hi2(zmk), hi2(ik))
-                    }
+                    for(int q = 0; q < R; q += 2) COATI_ROWPAIR3_SGN(q, ZS)
                     outX = Xp[R - 1];
                     outY0 = Ycur[R - 3], outY1 = Ycur[R - 2], outY2 = Ycur[R - 1];
                     diagX = recvX;
@@ -209,7 +178,7 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     uint32_t w[WPL];
 #pragma unroll
                     for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
-                    if(SGN) {  // see viterbi_pipe1.cuh: align the pushed bits, complement planes 0-3
+                    {  // see viterbi_pipe1.cuh: align the pushed bits, complement planes 0-3
                         const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
                         const uint32_t sh = 31u - (t_end & 31u);
 #pragma unroll
@@ -223,6 +192,12 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
 #pragma unroll
                         for(int j = 0; j < 5; ++j) acc[q][j] = 0;
                 }
+                ++u;
+            };
+            for(uint32_t t = 0; t < nsteps; t += 3) {
+                step(std::integral_constant<int, 0>{}, t);
+                if(t + 1 < nsteps) step(std::integral_constant<int, 1>{}, t + 1);
+                if(t + 2 < nsteps) step(std::integral_constant<int, 2>{}, t + 2);
             }
             if(band == nbands - 1) {
                 const uint32_t rr = (la - 1) % H;
