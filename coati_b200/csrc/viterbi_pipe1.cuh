@@ -251,27 +251,30 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             uint32_t u = 0u - (uint32_t)lane;  // u = t - lane = c - 1
             __syncwarp();
 
-            for(uint32_t t = 0; t < nsteps; ++t, ++u) {
+            // blocks of 32 steps = one word of every decision plane; the flush sits between blocks
+            for(uint32_t t0 = 0; t0 < nsteps; t0 += 32) {
+              const uint32_t t1 = min(t0 + 32u, nsteps);
+              if(WAVE && t0 != 0) {  // block t0 / 32 becomes current; refill the next
+                  static_assert(WAVE_BLOCK == 32, "refill once per flush block");
+                  blkA = blkB, symA = symB;
+                  blkB = load_block(t0 + WAVE_BLOCK + 2);
+                  symB = b[min(t0 + WAVE_BLOCK + 1 + lane, lb - 1)];
+              }
+              const float2* pbin = bin + t0 + 2;  // lane 0's inputs for the NEXT step (column t + 2);
+              const uint8_t* pb = b + t0 + 1;     // both arrays are padded past column lb
+              for(uint32_t t = t0; t < t1; ++t, ++u) {
                 const float recvX = __shfl_sync(FULL, outX, rot);
                 const float recvY = __shfl_sync(FULL, outY, rot);
                 const uint32_t bo = __shfl_sync(FULL, boff, rot);
-                // lane 0's inputs for the NEXT step (column t + 2)
                 float2 bnv;
                 uint32_t bl;
                 if(WAVE) {
-                    constexpr uint32_t WB = WAVE_BLOCK;
-                    if((t & (WB - 1)) == 0 && t != 0) {  // block t / WB becomes current; refill the next
-                        blkA = blkB, symA = symB;
-                        blkB = load_block(t + WB + 2);
-                        symB = b[min(t + WB + 1 + lane, lb - 1)];
-                    }
-                    bnv.x = __shfl_sync(FULL, blkA.x, t & (WB - 1));
-                    bnv.y = __shfl_sync(FULL, blkA.y, t & (WB - 1));
-                    bl = __shfl_sync(FULL, symA, t & (WB - 1));
+                    bnv.x = __shfl_sync(FULL, blkA.x, t - t0);
+                    bnv.y = __shfl_sync(FULL, blkA.y, t - t0);
+                    bl = __shfl_sync(FULL, symA, t - t0);
                 } else {  // uniform addresses, written by this warp one band earlier
-                    const uint32_t cn = min(t + 2, lb);
-                    bnv = bin[cn];
-                    bl = b[cn - 1];
+                    bnv = *pbin++;
+                    bl = *pb++;
                 }
                 if(u < lb) {
                     const uint32_t bm = 1u << (31 - (t & 31));
@@ -312,8 +315,10 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     outX = bnv.x, outY = bnv.y;
                     boff = bl * 512u;
                 }
-                // ---- flush the 32-step block of decision planes ---------------------------------
-                if((t & 31) == 31 || t == nsteps - 1) {
+              }
+              // ---- flush the 32-step block of decision planes ---------------------------------
+              {
+                    const uint32_t t = t1 - 1;  // last step of the block
                     uint4* dst = dir + ((size_t)(band * nblocks + (t >> 5)) * 32 + lane) * (WPL / 4);
                     uint32_t w[WPL];
 #pragma unroll
@@ -333,7 +338,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     for(int q = 0; q < R; ++q)
 #pragma unroll
                         for(int j = 0; j < 5; ++j) acc[q][j] = 0;
-                }
+              }
             }
             // Viterbi score = X(La, Lb): max3 of the adjusted terminal scores (align_pair.cc:130-138,265)
             if(band == nbands - 1) {
