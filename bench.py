@@ -353,6 +353,18 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM bytes of the fill launches per step, from the committed ncu capture (bytes per cell there x cells here)
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
+            tj = json.load(fh).get(args.workload, {})
+        if "bytes_per_cell" in tj:
+            traffic = tj["bytes_per_cell"] * cells  # bytes per step, all fill launches of one GPU
+            traffic_note = ("DRAM bytes of the fill launches per step and GPU: %.4f B/cell measured by ncu --set full "
+                            "(profiles/r01_traffic.json) x cells; algorithmic decision stream 0.625 B/cell"
+                            % tj["bytes_per_cell"])
+    except (OSError, ValueError):
+        pass
     line = {
         "metric": "mar-mg Viterbi GCUPS (fill + traceback)", "value": value, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -372,7 +384,7 @@ def main():
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops if peak_tflops else None,
                      "peak_at_max_clock": peak_tflops_max, "flop_per_cell": FLOP_PER_CELL,
                      "kernel_ms_per_step": fill_ms, "kernel_gcups": cells / (fill_ms / 1e3) / 1e9 if fill_ms else None,
-                     "traffic": None,
+                     "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": f"{info['sm_count']} SMs x 128 FP32 lanes x median SM clock under load",
                      "hbm_stream": {"achieved_gbs": stats["dir_bytes"] / (fill_ms / 1e3) / 1e9 if fill_ms else None,
                                     "peak_gbs": hbm_peak, "of": "measured" if peaks else "fallback"},

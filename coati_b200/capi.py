@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import time
 import os
 
 import numpy as np
@@ -218,8 +219,11 @@ class Forward:
         sc = np.zeros(max(n, 1), dtype=np.float32)
         st = (C.c_uint64 * 2)(int(state[0]), int(state[1]))
         ms = C.c_float(0)
-        self.ctx._check(self.lib.coati_gpu_sampleback(self.h, anc.encode("latin-1"), des.encode("latin-1"), st, n,
+        anc_b, des_b = anc.encode("latin-1"), des.encode("latin-1")
+        t0 = time.perf_counter()
+        self.ctx._check(self.lib.coati_gpu_sampleback(self.h, anc_b, des_b, st, n,
                                                       _vp(oa), _vp(ob), ol, sc.ctypes.data_as(_fp), C.byref(ms)))
+        self.last_call_s = time.perf_counter() - t0  # the C-ABI call alone (kernels + D2H), no Python decoding
         rows = [(oa[s * stride:s * stride + ol[s]].tobytes().decode("latin-1"),
                  ob[s * stride:s * stride + ol[s]].tobytes().decode("latin-1")) for s in range(n)]
         return rows, sc[:n], np.array([st[0], st[1]], dtype=np.uint64), ms.value

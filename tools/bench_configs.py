@@ -92,7 +92,8 @@ def main():
         first_bad = next((i for i, (x, y) in enumerate(zip(rows, orows)) if x != y), None)
         print(json.dumps({"case": "C2 example-003 sample -n 1000 -s random42", "la": len(a), "lb": len(b),
                           "gpu_forward_kernel_ms": fill_ms, "gpu_forward_e2e_ms": 1e3 * (t1 - t0),
-                          "gpu_sampleback_kernel_ms": smp_ms, "gpu_sampleback_e2e_ms": 1e3 * (t2 - t1),
+                          "gpu_sampleback_kernel_ms": smp_ms, "gpu_sampleback_cabi_ms": 1e3 * fw.last_call_s,
+                          "gpu_sampleback_python_e2e_ms": 1e3 * (t2 - t1),
                           "cpu_forward_ms": 1e3 * tm.get("fill_s", 0), "cpu_sampleback_ms": 1e3 * tm.get("sample_s", 0),
                           "sample_match_rate": match / 1000.0, "first_mismatch": first_bad,
                           "rng_state_identical": bool(np.array_equal(st2, ost))}), flush=True)
