@@ -197,10 +197,22 @@ def run_reference(args, wl, table):
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
+def emit(line):
+    """The JSON line is the LAST line of stdout: flush whatever C libraries (NCCL's version banner) still
+    hold in their stdio buffers first."""
+    sys.stdout.flush()
+    try:
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+    except Exception:
+        pass
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
@@ -397,7 +409,7 @@ def main():
                 if k in ("value", "unit", "cores", "kind", "sample", "pairs_per_s")}
         except Exception as ex:  # the checker failing must not hide the measurement
             line["cpu_baseline"] = {"error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

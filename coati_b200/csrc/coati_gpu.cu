@@ -67,7 +67,7 @@ struct DevPool {
         // find it big enough (cudaMalloc synchronises the device: a miss stalls the pipeline)
         void* p = nullptr;
         trace_mark("    pool miss (MiB)", bytes >> 20);
-        size_t padded = (bytes + bytes / 8 + 511) & ~size_t(511);
+        size_t padded = (bytes + std::min<size_t>(bytes / 8, size_t(1) << 30) + 511) & ~size_t(511);
         *err = cudaMalloc(&p, padded);
         if(*err != cudaSuccess) {
             cudaGetLastError();
