@@ -161,6 +161,7 @@ struct coati_gpu_ctx {
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
     bool force_generic = false, no_wave = false;
+    uint32_t force_r = 0;  // COATI_GPU_FORCE_R: rows per lane of every inter-pair fill (tuning)
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
     DevPool pool;
     HostPool hpool;
@@ -270,7 +271,8 @@ PipeCfg make_cfg3() {  // K = 3: FADD2 specialisation (viterbi_pipe3.cuh)
 PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false, 16>(), make_cfg1<8, false, 16>(), make_cfg<3, 3>(),
                          make_cfg3<6, 16>(),        make_cfg1<2, true, 16>(),  make_cfg1<4, true, 16>(),
                          make_cfg1<8, true, 16>(),  make_cfg1<4, false, 4>(),  make_cfg1<8, false, 4>(),
-                         make_cfg1<8, true, 4>(),   make_cfg3<6, 4>()};
+                         make_cfg1<8, true, 4>(),   make_cfg3<6, 4>(),         make_cfg1<10, false, 16>(),
+                         make_cfg1<10, false, 4>(), make_cfg1<10, true, 16>(),  make_cfg1<10, true, 4>()};
 
 // nc = 4 picks the ACGT-only variant when it exists, else falls back to the 16-column kernel
 const PipeCfg* find_cfg(uint32_t k, uint32_t cfg, uint32_t nc = 16) {
@@ -283,10 +285,14 @@ const PipeCfg* find_cfg(uint32_t k, uint32_t cfg, uint32_t nc = 16) {
     return fallback;
 }
 
-// issue-slot model of one pair on one warp: bands x steps x (R cells + per-step overhead)
+// issue-slot model of one pair on one warp: bands x steps x instructions per step (SASS counts of the
+// step loops, tools/sass_count.py: 108 / 179 / 217 at R = 4 / 8 / 10), weighted by the issue efficiency the
+// resident warps of that configuration reach (8 / 5 / 4 CTAs per SM); checked against whole-workload runs
+// of each configuration alone: 1004 / 963 / 1065 GCUPS on C5
 double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
     const double nbands = (la + 32 * R - 1) / (32 * R);
-    return nbands * (lb + 31.0) * (R * 22.0 + 18.0);
+    const double eff = R <= 4 ? 0.81 : 0.70;  // measured per-configuration C5 runs (COATI_GPU_FORCE_R)
+    return nbands * (lb + 31.0) * (R * 18.0 + 35.0) / eff;
 }
 
 }  // namespace
@@ -400,9 +406,10 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
         }
     }
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_FORCE_R")) ctx->force_r = (uint32_t)std::atoi(env);
     if(const char* env = std::getenv("COATI_GPU_WAVE_R")) {
         const uint32_t r = (uint32_t)std::atoi(env);
-        if(r == 2 || r == 4 || r == 8) ctx->wave_r = r;
+        if(r == 2 || r == 4 || r == 8 || r == 10) ctx->wave_r = r;
     }
     for(PipeCfg& pc : g_pipe_cfgs) {
         if(cudaFuncSetAttribute(pc.entry(), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -588,7 +595,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
         if(!ctx->force_generic && la > 0 && lb > 0) {
             double best = 0;
             for(const PipeCfg& pc : g_pipe_cfgs) {
-                if(pc.k != k || pc.wave) continue;
+                if(pc.k != k || pc.wave || (ctx->force_r && pc.R != ctx->force_r)) continue;
                 const double c = pipe_cost(d.la, d.lb, pc.R);
                 if(d.cfg == 0 || c < best) best = c, d.cfg = pc.R;
             }
@@ -597,11 +604,10 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
             const bool small_batch = npairs < 2048;
             if(k == 1 && !ctx->no_wave && la >= 1024 && lb >= 512 &&
                (cells >= (1ull << 26) || (small_batch && cells >= (1ull << 21)))) {
-                const uint64_t nb8 = (la + 255) / 256, nb4 = (la + 127) / 128;
-                // measured on B200 (tools/wave_exp.py): the systolic chain is latency bound per step, so
-                // the widest lane tile wins at every length from 10k to 160k
-                (void)nb8, (void)nb4;
-                d.cfg = (la <= 100000 ? 4u : 8u) | CFG_WAVE;
+                // measured on B200 (tools/wave_exp.py, tools/long_pair.py): the systolic chain is latency
+                // bound per step, so wide lane tiles win once there are enough bands to fill the GPU:
+                // fill + traceback at 40k: 18.4 ms (R = 4) / 21.0 (R = 10); at 160k: 99 / 91 (R = 8) / 86
+                d.cfg = (la <= 100000 ? 4u : 10u) | CFG_WAVE;
                 if(ctx->wave_r) d.cfg = ctx->wave_r | CFG_WAVE;
             }
         }
@@ -927,6 +933,7 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
             case 2: COATI_TB(2) break;
             case 4: COATI_TB(4) break;
             case 8: COATI_TB(8) break;
+            case 10: COATI_TB(10) break;
             default: return COATI_GPU_E_ARG;
             }
 #undef COATI_TB

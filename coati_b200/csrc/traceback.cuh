@@ -233,6 +233,7 @@ traceback_chunk_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint3
     case 4: traceback_walk<PipeLayoutR<4>, false>(pd, dirs, gap, out_b, res); break;
     case 6: traceback_walk<PipeLayoutR<6>, false>(pd, dirs, gap, out_b, res); break;
     case 8: traceback_walk<PipeLayoutR<8>, false>(pd, dirs, gap, out_b, res); break;
+    case 10: traceback_walk<PipeLayoutR<10>, false>(pd, dirs, gap, out_b, res); break;
     default: res.status = -8; res.len = 0; res.start = pd.la + pd.lb; break;
     }
 }

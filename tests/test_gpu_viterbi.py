@@ -291,3 +291,44 @@ def test_per_pair_models_leaf_batch(k, force_generic, tables):
     with pytest.raises(coati_b200.CoatiGpuError):
         ctx.viterbi_batch(PackedPairs(As[:2], Bs[:2], ancs[:2], dess[:2]), model_idx=[0, 3])
     ctx.close()
+
+
+@pytest.mark.parametrize("nsub", [2, 3, 7])
+def test_pipelined_lanes_equal_single_call(nsub, tables):
+    """The sub-batch pipeline (three lanes, fills on their own low-priority streams, event fences) gives the
+    rows, scores and per-pair status of the plain call: forced on a small batch with COATI_GPU_NSUB, for the
+    encoded, the per-pair-model and the raw-sequence entry points, error pairs included."""
+    import coati_b200
+    rng = np.random.RandomState(100 + nsub)
+    names = ["mg_golden", "ecm_default"]
+    T = np.stack([tables[n] for n in names])
+    ancs, dess, As, Bs = _random_batch(rng, 151, 1, 90)
+    model = rng.randint(0, 2, size=151)
+    raw_a = list(ancs) + ["AAACCNGGG", "AAATAAGGG", "AAAC"]
+    raw_d = list(dess) + ["AAACCC", "AAACCC", "AAA"]
+    for i in range(0, 151, 5):  # a few end stops, so trimming / restoring happens inside sub-batches
+        raw_a[i] += "TAA"
+    perm = rng.permutation(len(raw_a))
+    raw_a, raw_d = [raw_a[i] for i in perm], [raw_d[i] for i in perm]
+    ctx = coati_b200.Context(0)
+    ctx.set_models(T, oracle.DEFAULT_G, oracle.DEFAULT_E, 1)
+    pack = PackedPairs(As, Bs, ancs, dess)
+    outs = []
+    for n in (1, nsub):
+        os.environ["COATI_GPU_NSUB"] = str(n)
+        try:
+            outs.append((ctx.viterbi_batch(pack), ctx.viterbi_batch(pack, model_idx=model),
+                         ctx.alignpair_batch(raw_a, raw_d)))
+        finally:
+            del os.environ["COATI_GPU_NSUB"]
+    for one, piped in zip(outs[0], outs[1]):
+        assert one[0] == piped[0] and one[1] == piped[1]
+        assert np.array_equal(one[2].view(np.uint32), piped[2].view(np.uint32))
+        assert np.array_equal(one[3], piped[3])
+    # and the plain call is right (oracle, per-pair table)
+    rows_a, rows_b, score, status = outs[1][1]
+    for p in range(0, 151, 7):
+        oa, ob, osc = oracle.viterbi(ancs[p], dess[p], tables[names[model[p]]], k=1, enc=(As[p], Bs[p]))
+        assert (rows_a[p], rows_b[p]) == (oa, ob) and util.f32_bits(score[p]) == util.f32_bits(osc), p
+    assert sorted(outs[1][2][3])[:3] == [-7, -6, -5]
+    ctx.close()
