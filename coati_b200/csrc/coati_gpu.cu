@@ -161,6 +161,7 @@ struct coati_gpu_ctx {
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
     bool force_generic = false, no_wave = false;
+    bool tb_serial = false;  // COATI_GPU_TB_SERIAL=1: long pairs walked one column at a time (A/B)
     uint32_t force_r = 0;  // COATI_GPU_FORCE_R: rows per lane of every inter-pair fill (tuning)
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
     DevPool pool;
@@ -234,6 +235,8 @@ struct Chunk {
 // a run of pairs inside a chunk that share one kernel configuration
 struct Run {
     uint32_t first, last, cfg, chunk;
+    uint64_t ops_off = 0;  // long pairs: op bytes and checkpoints of the segment-parallel expansion
+    uint32_t ck_off = 0;
 };
 
 // ---- pipelined-kernel registry ------------------------------------------------------------------
@@ -316,6 +319,8 @@ struct coati_gpu_batch {
     DevBuf<float> d_ring;
     DevBuf<float4> d_bnd;
     DevBuf<uint32_t> d_prog;
+    DevBuf<char> d_long_ops;
+    DevBuf<uint4> d_long_ck;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
     uint32_t nc = 16;  // 4 when every descendant symbol of the batch is A/C/G/T (set at upload)
     bool raw = false;  // raw-sequence batch: symbols are encoded on the device
@@ -406,6 +411,7 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
         }
     }
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_TB_SERIAL")) ctx->tb_serial = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_FORCE_R")) ctx->force_r = (uint32_t)std::atoi(env);
     if(const char* env = std::getenv("COATI_GPU_WAVE_R")) {
         const uint32_t r = (uint32_t)std::atoi(env);
@@ -746,6 +752,18 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
     ok(bt->d_bnd.alloc(std::max<uint64_t>((uint64_t)bt->bnd_ctas * PIPE_WARPS * 2 * bt->bnd_stride, wave_f4),
                        &ctx->pool));
     ok(bt->d_prog.alloc(wave_bands ? wave_bands + 2 : 0, &ctx->pool));
+    {
+        uint64_t ops_total = 0, ck_total = 0;
+        for(Run& r : bt->runs)
+            if(r.cfg & CFG_WAVE) {
+                const PairDesc& d = bt->descs[r.first];
+                r.ops_off = ops_total, r.ck_off = (uint32_t)ck_total;
+                ops_total += ((uint64_t)d.la + d.lb + 64) & ~63ull;
+                ck_total += long_ck_capacity(d.la, d.lb);
+            }
+        ok(bt->d_long_ops.alloc(ops_total, &ctx->pool));
+        ok(bt->d_long_ck.alloc(ck_total, &ctx->pool));
+    }
     ok(bt->d_dirs.alloc(need_max + 128, &ctx->pool));
     ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride, &ctx->pool));
     if(e != cudaSuccess) {
@@ -927,8 +945,13 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
             if(!(r.cfg & CFG_WAVE)) continue;
             const uint32_t cnt = r.last - r.first;
 #define COATI_TB(RR)                                                                                   \
-    traceback_kernel<PipeLayoutR<RR>, true><<<cnt, 32, 0, s>>>(                                        \
-        bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);
+    if(ctx->tb_serial)                                                                                 \
+        traceback_kernel<PipeLayoutR<RR>, true><<<cnt, 32, 0, s>>>(                                    \
+            bt->d_pairs.p, r.first, r.last, bt->d_dirs.p, ctx->gap, bt->d_out_b.p, bt->d_results.p);   \
+    else                                                                                               \
+        traceback_burst_kernel<PipeLayoutR<RR>><<<1, 32, 0, s>>>(                                      \
+            bt->d_pairs.p, r.first, bt->d_dirs.p, ctx->gap, bt->d_long_ops.p + r.ops_off,              \
+            bt->d_long_ck.p + r.ck_off, bt->d_results.p);
             switch(r.cfg & 0xffu) {
             case 2: COATI_TB(2) break;
             case 4: COATI_TB(4) break;
@@ -938,6 +961,15 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
             }
 #undef COATI_TB
             ++bt->launches;
+            if(!ctx->tb_serial) {  // rows of the long pair, one warp per >= 2048-column segment
+                const PairDesc& d = bt->descs[r.first];
+                const uint32_t nseg = long_ck_capacity(d.la, d.lb);
+                expand_long_kernel<<<(nseg + 1) / 2, 64, 0, s>>>(
+                    bt->d_pairs.p, r.first, bt->d_long_ops.p + r.ops_off, bt->d_long_ck.p + r.ck_off,
+                    bt->d_anc.p, bt->d_des.p, bt->d_out_a.p, bt->d_out_b.p, bt->d_results.p,
+                    ctx->gap.stop_gap);
+                ++bt->launches;
+            }
         }
         const uint32_t ccnt = ch.last - ch.first;
         if(any_inter) {
@@ -950,7 +982,8 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
         cudaEventRecord(cev[2], s);
         expand_rows_kernel<<<(ccnt + 1) / 2, 64, 0, s>>>(bt->d_pairs.p, ch.first, ch.last, bt->d_anc.p,
                                                          bt->d_des.p, bt->d_out_a.p, bt->d_out_b.p,
-                                                         bt->d_results.p, ctx->gap.stop_gap);
+                                                         bt->d_results.p, ctx->gap.stop_gap,
+                                                         ctx->tb_serial ? 0u : 1u);
         cudaEventRecord(cev[3], s);
         ++bt->launches;
     }

@@ -83,6 +83,7 @@ struct PipeLayout {
         case 3: return PipeLayoutR<3>::next(dir, pd, st, r, c);
         case 4: return PipeLayoutR<4>::next(dir, pd, st, r, c);
         case 6: return PipeLayoutR<6>::next(dir, pd, st, r, c);
+        case 10: return PipeLayoutR<10>::next(dir, pd, st, r, c);
         default: return PipeLayoutR<8>::next(dir, pd, st, r, c);
         }
     }
@@ -211,6 +212,91 @@ traceback_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t la
     traceback_walk<Layout, WARP>(pd, dirs, gap, out_b, res);
 }
 
+constexpr uint32_t LONG_SEG = 2048;  // columns per independently expanded segment of a long alignment
+__host__ __device__ inline uint32_t long_ck_capacity(uint32_t la, uint32_t lb) {
+    return (la + lb) / LONG_SEG + 8;  // header + one entry per segment boundary (+ margins, ends)
+}
+
+// Long pairs (k = 1): one warp per pair, RUNS of equal moves taken in one round.  In state st at (r, c)
+// the next 32 cells along the state's own direction -- diagonal for MATCH, up for DELETION, left for
+// INSERTION -- are decoded by the 32 lanes at once (lane j: the state the walk would be in after j + 1
+// such moves); a ballot gives the length of the run, its op bytes are written by the lanes in parallel
+// and the warp jumps to the end of the run.  The serial chain of the reference's loop
+// (align_pair.cc:268-299: index -> load -> decode -> move, once per column) becomes one round per run,
+// and the 32 loads of a round are independent.  Every round the lanes also touch the decision words
+// 32 + 8j steps further down the current diagonal, so the rounds find their words in L1 / L2.
+template <class Layout>
+__global__ void __launch_bounds__(32)
+traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uint8_t* __restrict__ dirs,
+                       GapConsts gap, char* __restrict__ ops, uint4* __restrict__ ck,
+                       PairResult* __restrict__ results) {
+    const uint32_t lane = threadIdx.x;
+    const PairDesc pd = pairs[p];
+    PairResult& res = results[pd.orig];
+    if(lane == 0) ck[0] = make_uint4(0, 0, 0, 0);
+    if(res.status != 0) return;
+    const uint32_t la = pd.la, lb = pd.lb;
+    const uint8_t* dir = dirs + pd.dir_off;
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t r = la, c = lb, pos = la + lb, round = 0, sink = 0;
+    // checkpoints (pos, r, c) every >= LONG_SEG columns: ops[pos] is the column that consumes anc[r] /
+    // des[c], so expand_long_kernel can expand the segments between checkpoints independently
+    uint32_t n_ck = 0, last_ck = pos;
+    auto mark = [&](uint32_t ps, uint32_t rr, uint32_t cc) {
+        if(lane == 0) ck[1 + n_ck] = make_uint4(ps, rr, cc, 0);
+        ++n_ck;
+        last_ck = ps;
+    };
+    mark(pos, r, c);
+    if(la == 0 || lb == 0) {  // no body cell: the path is the margin itself (align_pair.cc:82-90, 130-138)
+        const GapConsts g = gap;
+        if(lane == 0)
+            res.score = la == 0 && lb == 0 ? (0.0f + g.ng) + g.ng
+                        : la == 0          ? ((g.go + g.ge * (float)(lb - 1)) + g.gs) + g.ng
+                                           : ((g.ng + g.go) + g.ge * (float)(la - 1)) + g.gs;
+    }
+    int st = (la == 0 || lb == 0) ? ST_M : Layout::initial(dir, pd, res);
+    if(la > 0 && lb > 0)
+    for(;;) {
+        const uint32_t dr = st != ST_I, dc = st != ST_D, j1 = lane + 1;
+        const bool valid = dr * j1 < r + (1u - dr) && dc * j1 < c + (1u - dc);  // lands inside the body
+        int sj = -1;
+        if(valid) sj = Layout::next(dir, pd, st, r - dr * j1, c - dc * j1);
+        const uint32_t same = __ballot_sync(FULL, sj == st);
+        const uint32_t run = same == FULL ? 32u : (uint32_t)__ffs(~same);  // moves of this round (>= 1)
+        if(lane < run) ops[pos - 1 - lane] = (char)st;
+        pos -= run, r -= dr * run, c -= dc * run;
+        if(r == 0 || c == 0) break;
+        st = __shfl_sync(FULL, sj, run - 1);
+        if(pos + LONG_SEG <= last_ck) mark(pos, r, c);
+        if((round++ & 1) == 0) {
+            const uint32_t ahead = 32 + 8 * lane;
+            if(r > ahead && c > ahead) sink ^= Layout::touch(dir, pd, r - ahead, c - ahead);
+        }
+    }
+    // margins: only one state is finite there (align_pair.cc:84-90)
+    while(c > 0) {
+        const uint32_t m = min(c, LONG_SEG);
+        if(pos != last_ck) mark(pos, r, c);
+        for(uint32_t x = lane; x < m; x += 32) ops[pos - 1 - x] = ST_I;
+        pos -= m, c -= m;
+    }
+    while(r > 0) {
+        const uint32_t m = min(r, LONG_SEG);
+        if(pos != last_ck) mark(pos, r, c);
+        for(uint32_t x = lane; x < m; x += 32) ops[pos - 1 - x] = ST_D;
+        pos -= m, r -= m;
+    }
+    if(pos != last_ck) mark(pos, 0, 0);
+    if(lane == 0) {
+        ck[0] = make_uint4(n_ck, 0, 0, 0);
+        res.len = la + lb - pos;
+        res.start = pos;
+    } else if(sink == 0x9e3779b9u) {
+        res.pad = sink;  // keeps the read-ahead loads alive; never true in practice
+    }
+}
+
 // One thread per pair over a whole chunk of inter-pair runs: the layout follows the pair's own kernel
 // configuration (rows per lane R, or 0 for the anti-diagonal layout of the generic kernel), so all the
 // walks of a chunk -- each a serial, latency-bound chain -- are in flight together instead of one
@@ -249,11 +335,12 @@ __global__ void __launch_bounds__(64, 32)
 expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                                    const char* __restrict__ anc_all, const char* __restrict__ des_all,
                                    char* __restrict__ out_a, char* __restrict__ out_b,
-                                   PairResult* __restrict__ results, float stop_gap) {
+                                   PairResult* __restrict__ results, float stop_gap, uint32_t skip_long) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t p = first + warp;
     if(p >= last) return;
     const PairDesc pd = pairs[p];
+    if(skip_long && (pd.cfg & CFG_WAVE)) return;  // expanded segment-wise by expand_long_kernel
     const PairResult res = results[pd.orig];
     const char* anc = anc_all + pd.a_off;
     const char* des = des_all + pd.b_off;
@@ -298,6 +385,61 @@ expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t 
         oa[n] = 0;
         ob[n] = 0;
     }
+}
+
+// Long pairs: one warp per segment between two checkpoints of traceback_burst_kernel (ops in `ops`, rows
+// written left-aligned into the pair's output slots); the warp of the last segment also restores the end
+// stops and terminates the rows, as expand_rows_kernel does.
+__global__ void __launch_bounds__(64, 32)
+expand_long_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const char* __restrict__ ops,
+                   const uint4* __restrict__ ck, const char* __restrict__ anc_all,
+                   const char* __restrict__ des_all, char* __restrict__ out_a, char* __restrict__ out_b,
+                   PairResult* __restrict__ results, float stop_gap) {
+    const uint32_t seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const PairDesc pd = pairs[p];
+    const PairResult res = results[pd.orig];
+    const char* anc = anc_all + pd.a_off;
+    const char* des = des_all + pd.b_off;
+    char* oa = out_a + pd.out_off;
+    char* ob = out_b + pd.out_off;
+    const uint32_t n_ck = ck[0].x;
+    if(res.status != 0) {
+        if(seg == 0 && lane == 0) oa[0] = 0, ob[0] = 0;
+        return;
+    }
+    if(seg + 1 >= n_ck && seg != 0) return;
+    const bool body = seg + 1 < n_ck;
+    const uint4 hi = body ? ck[1 + seg] : make_uint4(0, 0, 0, 0);  // columns [lo.x, hi.x),
+    const uint4 lo = body ? ck[2 + seg] : make_uint4(0, 0, 0, 0);  // sources from (lo.y, lo.z)
+    const uint32_t start = res.start, lt = (1u << lane) - 1u;
+    uint32_t ia = lo.y, ib = lo.z;
+    for(uint32_t base = lo.x; base < hi.x; base += 32) {
+        const uint32_t x = base + lane;
+        const int op = x < hi.x ? ops[x] : -1;
+        const bool useA = op == ST_M || op == ST_D, useB = op == ST_M || op == ST_I;
+        const uint32_t ma = __ballot_sync(0xffffffffu, useA), mb = __ballot_sync(0xffffffffu, useB);
+        if(x < hi.x) {
+            oa[x - start] = useA ? anc[ia + __popc(ma & lt)] : '-';
+            ob[x - start] = useB ? des[ib + __popc(mb & lt)] : '-';
+        }
+        ia += __popc(ma);
+        ib += __popc(mb);
+    }
+    if(seg != 0) return;
+    uint32_t n = res.len;
+    const bool sa = pd.cfg & CFG_STOP_A, sb = pd.cfg & CFG_STOP_B;
+    if(sa || sb) {  // restore_end_stops (utils.cc:1044-1063), see expand_rows_kernel
+        if(lane < 3) {
+            oa[n + lane] = sa ? anc[pd.la + lane] : '-';
+            ob[n + lane] = sb ? des[pd.lb + lane] : '-';
+        }
+        if(lane == 0) {
+            results[pd.orig].len = n + 3;
+            if(sa != sb) results[pd.orig].score = res.score + stop_gap;
+        }
+        n += 3;
+    }
+    if(lane == 0) oa[n] = 0, ob[n] = 0;
 }
 
 // Raw-sequence entry point: marginal_seq_encoding (utils.cc:496-528) on the device, one warp per pair.
