@@ -7,6 +7,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "viterbi_pipe.cuh"
 
 namespace coati_gpu {
 
@@ -32,14 +33,14 @@ struct DiagLayout {
 // constant so the index arithmetic of the serial walk is shifts and masks, not integer divisions.
 template <int R>
 struct PipeLayoutR {
-    static constexpr uint32_t H = 32 * R, WPL = (5 * R + 3) & ~3u;
+    static constexpr uint32_t H = 32 * R, WPL = (5 * R + 3) & ~3u, BS = pipe_block_steps(R);
     __device__ __forceinline__ static uint64_t word_index(const PairDesc& pd, uint32_t r, uint32_t c,
                                                           uint32_t& shift) {
         const uint32_t band = (r - 1) / H, rr = (r - 1) % H, lane = rr / R, q = rr % R;
-        const uint32_t t = (c - 1) + lane, nblocks = (pd.lb + 62) / 32;
-        shift = 31 - (t & 31);
+        const uint32_t t = (c - 1) + lane, nblocks = (pd.lb + 31 + BS - 1) / BS;
+        shift = 31 - (t % BS);
         // one widening multiply; the in-block part stays 32-bit
-        return (uint64_t)(band * nblocks + (t >> 5)) * (32u * WPL) + (lane * WPL + q * 5);
+        return (uint64_t)(band * nblocks + t / BS) * (32u * WPL) + (lane * WPL + q * 5);
     }
     __device__ __forceinline__ static int next(const uint8_t* dir, const PairDesc& pd, int st,
                                                uint32_t r, uint32_t c) {

@@ -25,13 +25,18 @@ namespace coati_gpu {
 // ---- direction-stream layout of the pipelined kernels -------------------------------------------
 // planes: 0: xm == X (MATCH lands -> M)   1: xd == X (-> D, if plane 0 clear; else I)
 //         2: ym == Y (DELETION lands)     3: yd == Y            4: zm > zi (INSERTION lands -> M)
-// word index = ((band * nblocks + step/32) * 32 + lane) * WPL + q * 5 + plane, bit 31 - step%32,
-// step = (c - 1) + lane, lane = ((r-1) % H) / R, q = (r-1) % R.
+// word index = ((band * nblocks + step/BS) * 32 + lane) * WPL + q * 5 + plane, bit 31 - step%BS,
+// step = (c - 1) + lane, lane = ((r-1) % H) / R, q = (r-1) % R.  BS = steps per word: 32, or 30 for the
+// K = 3 configurations (R = 3, 6), whose step loop is unrolled three times (viterbi_pipe3.cuh) and
+// wants whole triples between two flushes.
 __host__ __device__ __forceinline__ uint32_t pipe_wpl(uint32_t R) { return (5 * R + 3) & ~3u; }
-__host__ __device__ __forceinline__ uint32_t pipe_nblocks(uint32_t lb) { return (lb + 31 + 31) / 32; }
+__host__ __device__ constexpr uint32_t pipe_block_steps(uint32_t R) { return R % 3 == 0 ? 30u : 32u; }
+__host__ __device__ __forceinline__ uint32_t pipe_nblocks(uint32_t lb, uint32_t R) {
+    return (lb + 31 + pipe_block_steps(R) - 1) / pipe_block_steps(R);
+}
 __host__ __device__ __forceinline__ uint64_t pipe_dir_bytes(uint32_t la, uint32_t lb, uint32_t R) {
     const uint64_t nbands = (la + 32 * R - 1) / (32 * R);
-    return nbands * pipe_nblocks(lb) * 32ull * pipe_wpl(R) * 4ull;
+    return nbands * pipe_nblocks(lb, R) * 32ull * pipe_wpl(R) * 4ull;
 }
 
 template <int K>
@@ -115,7 +120,8 @@ viterbi_pipe_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;
         uint4* dir = reinterpret_cast<uint4*>(dirs + pd.dir_off);
-        const uint32_t nblocks = pipe_nblocks(lb);
+        const uint32_t nblocks = pipe_nblocks(lb, R);
+        constexpr uint32_t BS = pipe_block_steps(R);
         const uint32_t nbands = (la + H - 1) / H;
         const uint32_t nsteps = lb + 31;
 
@@ -195,7 +201,7 @@ viterbi_pipe_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t
                 if(c + 1 >= 1 && c + 1 <= lb) bn = b[c];  // next step's symbol (c + 1)
                 if(active) {
                     // ---- R cells of column c ------------------------------------------------
-                    const uint32_t bm = 1u << (31 - (t & 31));
+                    const uint32_t bm = 1u << (31 - (t % BS));
                     float sv[R4 * 4];
 #pragma unroll
                     for(int h = 0; h < R4; ++h) {
@@ -232,8 +238,8 @@ viterbi_pipe_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t
                 }
                 bcode = bn;
                 // ---- flush the 32-step block of decision planes ---------------------------------
-                if((t & 31) == 31 || t == nsteps - 1) {
-                    uint4* dst = dir + ((size_t)(band * nblocks + (t >> 5)) * 32 + lane) * (WPL / 4);
+                if(t % BS == BS - 1 || t == nsteps - 1) {
+                    uint4* dst = dir + ((size_t)(band * nblocks + t / BS) * 32 + lane) * (WPL / 4);
                     uint32_t w[WPL];
 #pragma unroll
                     for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;

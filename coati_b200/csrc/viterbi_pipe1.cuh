@@ -168,7 +168,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;
         uint4* dir = reinterpret_cast<uint4*>(dirs + pd.dir_off);
-        const uint32_t nblocks = pipe_nblocks(lb);
+        const uint32_t nblocks = pipe_nblocks(lb, R);
         const uint32_t nbands = (la + H - 1) / H;
         const uint32_t nsteps = lb + 31;
         if(WAVE) {

@@ -84,7 +84,7 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         const uint8_t* a = a_all + pd.a_off;
         const uint8_t* b = b_all + pd.b_off;
         uint4* dir = reinterpret_cast<uint4*>(dirs + pd.dir_off);
-        const uint32_t nblocks = pipe_nblocks(lb);
+        const uint32_t nblocks = pipe_nblocks(lb, R);
         const uint32_t nbands = (la + H - 1) / H;
         const uint32_t nsteps = lb + 31;
 
@@ -138,16 +138,20 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
 
             // Z(r, c) is read three columns later: the history is a ring indexed by step % 3 (a lane's
             // steps are consecutive), fixed at compile time by unrolling the step loop three times
-            auto step = [&](auto zs_c, const uint32_t t) {
+            // The decision words hold BS = 30 steps, so a flush block is ten whole triples.
+            constexpr uint32_t BS = pipe_block_steps(R);
+            static_assert(BS % 3 == 0, "a flush block is a whole number of ring turns");
+            const float4* pbin = bin + 2;  // lane 0's inputs for the NEXT step (column t + 2); the row above
+            const uint8_t* pb = b + 1;     // and the symbols are padded past column lb
+            auto step = [&](auto zs_c) {
                 constexpr int ZS = decltype(zs_c)::value;
                 const float recvX = __shfl_sync(FULL, outX, rot);
                 recvY[0] = __shfl_sync(FULL, outY0, rot);
                 recvY[1] = __shfl_sync(FULL, outY1, rot);
                 recvY[2] = __shfl_sync(FULL, outY2, rot);
                 const uint32_t bo = __shfl_sync(FULL, boff, rot);
-                const uint32_t cn = min(t + 2, lb);
-                const float4 bnv = bin[cn];
-                const uint32_t bl = b[cn - 1];
+                const float4 bnv = *pbin++;
+                const uint32_t bl = *pb++;
                 if(u < lb) {
                     float sv[R4 * 4];
 #pragma unroll
@@ -173,31 +177,33 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     outX = bnv.x, outY0 = bnv.y, outY1 = bnv.z, outY2 = bnv.w;
                     boff = bl * 512u;
                 }
-                if((t & 31) == 31 || t == nsteps - 1) {
-                    uint4* dst = dir + ((size_t)(band * nblocks + (t >> 5)) * 32 + lane) * (WPL / 4);
-                    uint32_t w[WPL];
-#pragma unroll
-                    for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
-                    {  // see viterbi_pipe1.cuh: align the pushed bits, complement planes 0-3
-                        const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
-                        const uint32_t sh = 31u - (t_end & 31u);
-#pragma unroll
-                        for(int x = 0; x < 5 * R; ++x) w[x] = (x % 5 < 4 ? ~w[x] : w[x]) << sh;
-                    }
-#pragma unroll
-                    for(int x = 0; x < (int)WPL / 4; ++x)
-                        dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
-#pragma unroll
-                    for(int q = 0; q < R; ++q)
-#pragma unroll
-                        for(int j = 0; j < 5; ++j) acc[q][j] = 0;
-                }
                 ++u;
             };
-            for(uint32_t t = 0; t < nsteps; t += 3) {
-                step(std::integral_constant<int, 0>{}, t);
-                if(t + 1 < nsteps) step(std::integral_constant<int, 1>{}, t + 1);
-                if(t + 2 < nsteps) step(std::integral_constant<int, 2>{}, t + 2);
+            for(uint32_t t0 = 0; t0 < nsteps; t0 += BS) {
+                const uint32_t tn = min(BS, nsteps - t0);
+                for(uint32_t tt = 0; tt < tn; tt += 3) {
+                    step(std::integral_constant<int, 0>{});
+                    if(tt + 1 < tn) step(std::integral_constant<int, 1>{});
+                    if(tt + 2 < tn) step(std::integral_constant<int, 2>{});
+                }
+                // ---- flush the block of decision planes (see viterbi_pipe1.cuh: align the pushed bits,
+                // complement planes 0-3)
+                const uint32_t t = t0 + tn - 1;  // last step of the block
+                uint4* dst = dir + ((size_t)(band * nblocks + t0 / BS) * 32 + lane) * (WPL / 4);
+                uint32_t w[WPL];
+#pragma unroll
+                for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
+                const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
+                const uint32_t sh = 31u - (t_end % BS);
+#pragma unroll
+                for(int x = 0; x < 5 * R; ++x) w[x] = (x % 5 < 4 ? ~w[x] : w[x]) << sh;
+#pragma unroll
+                for(int x = 0; x < (int)WPL / 4; ++x)
+                    dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
+#pragma unroll
+                for(int q = 0; q < R; ++q)
+#pragma unroll
+                    for(int j = 0; j < 5; ++j) acc[q][j] = 0;
             }
             if(band == nbands - 1) {
                 const uint32_t rr = (la - 1) % H;
