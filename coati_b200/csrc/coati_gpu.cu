@@ -230,6 +230,7 @@ struct Chunk {
     uint32_t first, last;  // range in sorted order
     uint64_t dir_bytes;
     uint32_t max_la;
+    uint32_t long_first = 0, long_count = 0;  // its slice of the batch's list of warp-walked long pairs
 };
 
 // a run of pairs inside a chunk that share one kernel configuration
@@ -319,6 +320,8 @@ struct coati_gpu_batch {
     DevBuf<float> d_ring;
     DevBuf<float4> d_bnd;
     DevBuf<uint32_t> d_prog;
+    DevBuf<uint32_t> d_long_list;
+    std::vector<uint32_t> long_list;  // sorted indices of the batch pairs walked by traceback_burst_list_kernel
     DevBuf<char> d_long_ops;
     DevBuf<uint4> d_long_ck;
     uint32_t ring_stride = 0, ring_ctas = 0, bnd_stride = 0, bnd_ctas = 0;
@@ -763,6 +766,15 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
             }
         ok(bt->d_long_ops.alloc(ops_total, &ctx->pool));
         ok(bt->d_long_ck.alloc(ck_total, &ctx->pool));
+        if(!ctx->tb_serial)
+            for(Chunk& c : bt->chunks) {
+                c.long_first = (uint32_t)bt->long_list.size();
+                for(uint32_t x = c.first; x < c.last; ++x)
+                    if(bt->host_status[bt->descs[x].orig] == COATI_GPU_OK && burst_in_batch(bt->descs[x], k))
+                        bt->long_list.push_back(x);
+                c.long_count = (uint32_t)bt->long_list.size() - c.long_first;
+            }
+        ok(bt->d_long_list.alloc(bt->long_list.size(), &ctx->pool));
     }
     ok(bt->d_dirs.alloc(need_max + 128, &ctx->pool));
     ok(bt->d_ring.alloc((size_t)bt->ring_ctas * 3 * ring_depth(k) * bt->ring_stride, &ctx->pool));
@@ -776,6 +788,9 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_pairs.p, bt->descs.data(), npairs * sizeof(PairDesc),
                                     cudaMemcpyHostToDevice, bt->stream));  // descs outlive the copy (member)
     }
+    if(!bt->long_list.empty())
+        CU_TRY(ctx, cudaMemcpyAsync(bt->d_long_list.p, bt->long_list.data(), bt->long_list.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, bt->stream));
     trace_mark("  plan: descs H2D", npairs);
     *out = holder.release();
     return COATI_GPU_OK;
@@ -973,9 +988,15 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
         }
         const uint32_t ccnt = ch.last - ch.first;
         if(any_inter) {
+            if(ch.long_count) {
+                traceback_burst_list_kernel<<<(ch.long_count + 1) / 2, 64, 0, s>>>(
+                    bt->d_pairs.p, bt->d_long_list.p + ch.long_first, ch.long_count, bt->d_dirs.p, ctx->gap,
+                    bt->d_out_b.p, bt->d_results.p);
+                ++bt->launches;
+            }
             traceback_chunk_kernel<<<(ccnt + 63) / 64, 64, 0, s>>>(bt->d_pairs.p, ch.first, ch.last,
                                                                    bt->d_dirs.p, ctx->gap, bt->d_out_b.p,
-                                                                   bt->d_results.p);
+                                                                   bt->d_results.p, ctx->tb_serial ? 0u : 1u);
             ++bt->launches;
         }
         cudaEventRecord(cev[1], s);

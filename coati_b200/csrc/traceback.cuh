@@ -226,15 +226,14 @@ __host__ __device__ inline uint32_t long_ck_capacity(uint32_t la, uint32_t lb) {
 // (align_pair.cc:268-299: index -> load -> decode -> move, once per column) becomes one round per run,
 // and the 32 loads of a round are independent.  Every round the lanes also touch the decision words
 // 32 + 8j steps further down the current diagonal, so the rounds find their words in L1 / L2.
-template <class Layout>
-__global__ void __launch_bounds__(32)
-traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uint8_t* __restrict__ dirs,
-                       GapConsts gap, char* __restrict__ ops, uint4* __restrict__ ck,
-                       PairResult* __restrict__ results) {
-    const uint32_t lane = threadIdx.x;
-    const PairDesc pd = pairs[p];
-    PairResult& res = results[pd.orig];
-    if(lane == 0) ck[0] = make_uint4(0, 0, 0, 0);
+// CK: record checkpoints for expand_long_kernel (single long pairs); without them the op bytes go to
+// the pair's out_b slot and expand_rows_kernel builds the rows (long pairs inside a batch).
+template <class Layout, bool CK>
+__device__ __forceinline__ void traceback_burst_walk(const PairDesc& pd, const uint8_t* __restrict__ dirs,
+                                                     const GapConsts& gap, char* __restrict__ ops,
+                                                     uint4* __restrict__ ck, PairResult& res) {
+    const uint32_t lane = threadIdx.x & 31;
+    if(CK && lane == 0) ck[0] = make_uint4(0, 0, 0, 0);
     if(res.status != 0) return;
     const uint32_t la = pd.la, lb = pd.lb;
     const uint8_t* dir = dirs + pd.dir_off;
@@ -244,7 +243,7 @@ traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uin
     // des[c], so expand_long_kernel can expand the segments between checkpoints independently
     uint32_t n_ck = 0, last_ck = pos;
     auto mark = [&](uint32_t ps, uint32_t rr, uint32_t cc) {
-        if(lane == 0) ck[1 + n_ck] = make_uint4(ps, rr, cc, 0);
+        if(CK && lane == 0) ck[1 + n_ck] = make_uint4(ps, rr, cc, 0);
         ++n_ck;
         last_ck = ps;
     };
@@ -269,7 +268,7 @@ traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uin
         pos -= run, r -= dr * run, c -= dc * run;
         if(r == 0 || c == 0) break;
         st = __shfl_sync(FULL, sj, run - 1);
-        if(pos + LONG_SEG <= last_ck) mark(pos, r, c);
+        if(CK && pos + LONG_SEG <= last_ck) mark(pos, r, c);
         if((round++ & 1) == 0) {
             const uint32_t ahead = 32 + 8 * lane;
             if(r > ahead && c > ahead) sink ^= Layout::touch(dir, pd, r - ahead, c - ahead);
@@ -290,11 +289,45 @@ traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uin
     }
     if(pos != last_ck) mark(pos, 0, 0);
     if(lane == 0) {
-        ck[0] = make_uint4(n_ck, 0, 0, 0);
+        if(CK) ck[0] = make_uint4(n_ck, 0, 0, 0);
         res.len = la + lb - pos;
         res.start = pos;
     } else if(sink == 0x9e3779b9u) {
         res.pad = sink;  // keeps the read-ahead loads alive; never true in practice
+    }
+}
+
+template <class Layout>
+__global__ void __launch_bounds__(32)
+traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uint8_t* __restrict__ dirs,
+                       GapConsts gap, char* __restrict__ ops, uint4* __restrict__ ck,
+                       PairResult* __restrict__ results) {
+    const PairDesc pd = pairs[p];
+    traceback_burst_walk<Layout, true>(pd, dirs, gap, ops, ck, results[pd.orig]);
+}
+
+// The longest pairs of a batch (listed by the host): run-at-a-time walks, one warp per pair, so the
+// launch that walks the rest one thread per pair is not left waiting for a few thousand-column chains.
+constexpr uint32_t BURST_MIN_COLUMNS = 3000;  // la + lb from which a batch pair is walked by a warp
+__host__ __device__ inline bool burst_in_batch(const PairDesc& pd, uint32_t k) {
+    return k == 1 && (pd.cfg & 0xffu) != 0 && !(pd.cfg & CFG_WAVE) && pd.la > 0 && pd.lb > 0 &&
+           pd.la + pd.lb >= BURST_MIN_COLUMNS;
+}
+__global__ void __launch_bounds__(64)
+traceback_burst_list_kernel(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ list, uint32_t n,
+                            const uint8_t* __restrict__ dirs, GapConsts gap, char* __restrict__ out_b,
+                            PairResult* __restrict__ results) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if(w >= n) return;
+    const PairDesc pd = pairs[list[w]];
+    PairResult& res = results[pd.orig];
+    char* ops = out_b + pd.out_off;
+    switch(pd.cfg & 0xffu) {
+    case 2: traceback_burst_walk<PipeLayoutR<2>, false>(pd, dirs, gap, ops, nullptr, res); break;
+    case 4: traceback_burst_walk<PipeLayoutR<4>, false>(pd, dirs, gap, ops, nullptr, res); break;
+    case 8: traceback_burst_walk<PipeLayoutR<8>, false>(pd, dirs, gap, ops, nullptr, res); break;
+    case 10: traceback_burst_walk<PipeLayoutR<10>, false>(pd, dirs, gap, ops, nullptr, res); break;
+    default: break;  // not listed by the host
     }
 }
 
@@ -306,11 +339,12 @@ traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uin
 __global__ void __launch_bounds__(64, 32)
 traceback_chunk_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                        const uint8_t* __restrict__ dirs, GapConsts gap, char* __restrict__ out_b,
-                       PairResult* __restrict__ results) {
+                       PairResult* __restrict__ results, uint32_t burst) {
     const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= last) return;
     const PairDesc pd = pairs[p];
     if(pd.cfg & CFG_WAVE) return;  // long pairs: warp-per-pair launch with read-ahead
+    if(burst && burst_in_batch(pd, gap.k)) return;  // walked by traceback_burst_list_kernel
     PairResult& res = results[pd.orig];
     if(res.status != 0) return;
     switch(pd.cfg & 0xffu) {

@@ -204,12 +204,15 @@ def test_wavefront_kernel_equals_inter_pair_kernel(tables):
     a, b = oracle.encode_pair(anc, des)
     want = oracle.viterbi(anc, des, T, enc=(a, b))
     outs = []
-    for env in ("0", "1"):
-        os.environ["COATI_GPU_NO_WAVE"] = env
+    # wavefront fill or not; run-at-a-time warp traceback (default) or the column-at-a-time walk
+    for no_wave, tb_serial in (("0", "0"), ("1", "0"), ("0", "1"), ("1", "1")):
+        os.environ["COATI_GPU_NO_WAVE"] = no_wave
+        os.environ["COATI_GPU_TB_SERIAL"] = tb_serial
         try:
             ctx = coati_b200.Context(0)
         finally:
             del os.environ["COATI_GPU_NO_WAVE"]
+            del os.environ["COATI_GPU_TB_SERIAL"]
         ctx.set_model(T, oracle.DEFAULT_G, oracle.DEFAULT_E, 1)
         outs.append(ctx.viterbi(a, b, anc, des))
         # ragged mini-batch: a long pair next to short ones
