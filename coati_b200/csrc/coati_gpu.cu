@@ -1133,12 +1133,42 @@ static void scan_raw_pairs(uint32_t k, const char* anc_all, const uint64_t* anc_
     }
 }
 
+static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                  const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
+                                  const char* anc_all, const char* des_all, char* out_a, char* out_b,
+                                  uint64_t* out_len, float* score, int32_t* status, bool raw_mode,
+                                  const uint32_t* model, size_t nsub);
+
 static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
                               const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
                               const char* anc_all, const char* des_all, char* out_a, char* out_b,
                               uint64_t* out_len, float* score, int32_t* status, bool raw_mode,
                               const uint32_t* model = nullptr) {
     if(!ctx || (npairs && (!a_off || !b_off))) return COATI_GPU_E_ARG;
+    // Large batches are cut into sub-batches that rotate over the lanes of the context, so that the
+    // host-side planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its
+    // neighbours.
+    const size_t kMinPipe = 32768;
+    size_t nsub = 1;
+    if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(16, npairs / kMinPipe);
+    if(const char* env = std::getenv("COATI_GPU_NSUB")) nsub = std::max(1, std::atoi(env));  // tuning
+    if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
+    int rc = viterbi_batch_pipeline(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
+                                    out_len, score, status, raw_mode, model, nsub);
+    if(rc == COATI_GPU_E_NOMEM && nsub > 1) {
+        // a lane owns a third of the memory: a pair too big for that still fits the whole device
+        ctx->pool.trim();
+        rc = viterbi_batch_pipeline(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
+                                    out_len, score, status, raw_mode, model, 1);
+    }
+    return rc;
+}
+
+static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                  const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
+                                  const char* anc_all, const char* des_all, char* out_a, char* out_b,
+                                  uint64_t* out_len, float* score, int32_t* status, bool raw_mode,
+                                  const uint32_t* model, size_t nsub) {
     // raw pairs: the per-pair scan runs sub-batch by sub-batch, inside the pipeline
     std::vector<uint8_t> rawbuf;
     if(raw_mode) {
@@ -1149,13 +1179,6 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
         }
     }
     const uint8_t* raw = raw_mode ? rawbuf.data() : nullptr;
-    // Large batches are cut into sub-batches that alternate between two streams, so that the host-side
-    // planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its neighbours.
-    const size_t kMinPipe = 32768;
-    size_t nsub = 1;
-    if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(16, npairs / kMinPipe);
-    if(const char* env = std::getenv("COATI_GPU_NSUB")) nsub = std::max(1, std::atoi(env));  // tuning
-    if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
     constexpr int NSLOT = 3;  // sub-batches in flight: one finishing, one filling, one queued behind it
     coati_gpu_batch* bt[NSLOT] = {nullptr, nullptr, nullptr};
     size_t first[NSLOT] = {0, 0, 0};

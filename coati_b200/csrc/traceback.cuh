@@ -335,7 +335,8 @@ traceback_burst_list_kernel(const PairDesc* __restrict__ pairs, const uint32_t* 
 // configuration (rows per lane R, or 0 for the anti-diagonal layout of the generic kernel), so all the
 // walks of a chunk -- each a serial, latency-bound chain -- are in flight together instead of one
 // launch per configuration.  Pairs are sorted by configuration, so a warp rarely mixes two layouts.
-// 64 threads x 32 registers: small enough to be co-resident with the fill CTAs of the next sub-batch.
+// 64 threads x 32 registers per CTA: fits into the registers the resident fill CTAs of another pipeline
+// lane leave free.
 __global__ void __launch_bounds__(64, 32)
 traceback_chunk_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                        const uint8_t* __restrict__ dirs, GapConsts gap, char* __restrict__ out_b,

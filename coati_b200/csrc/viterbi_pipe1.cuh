@@ -1,13 +1,16 @@
 // K = 1 specialisation of the register-pipelined Viterbi fill (see viterbi_pipe.cuh for the scheme
 // and the exactness argument).  Same lattice decomposition, same decision-plane stream (PipeLayout),
 // tuned for issue slots on sm_100a:
-//   * the match/insert halves of two adjacent rows are evaluated with packed add.rn.f32x2 (FADD2):
-//     nine packed adds replace eighteen scalar ones per row pair; each lane of a packed add is an
-//     IEEE round-to-nearest FADD, so results are bit-identical to the scalar form;
-//   * decisions are FSETP + predicated OR into the plane accumulators (no select/mask pair);
+//   * the match/insert halves of two adjacent rows are evaluated with packed add.rn.f32x2 (FADD2); each
+//     lane of a packed add is an IEEE round-to-nearest FADD, so results are bit-identical to the scalar
+//     form;
+//   * decisions (SGN form, the default) are the sign bits of five packed subtractions per row pair,
+//     pushed into the plane accumulators by funnel shifts: 1.5 instructions per decision bit; the
+//     FSETP + predicated IMAD form (2 per bit) is kept as SGN = false for A/B runs;
 //   * the symbol, the row above the band and the row below it move on uniform addresses
 //     (lane 31 carries lane 0's inputs in its outgoing shuffle registers), so the per-step
-//     overhead is three shuffles, two broadcast loads and one predicated store.
+//     overhead is three shuffles, two broadcast loads and one predicated store;
+//   * the step loop runs in blocks of 32 steps (one word of every plane) with the flush between blocks.
 #pragma once
 
 #include "common.cuh"
