@@ -1,3 +1,5 @@
+"""Host-side gaps (> 12 ms between two marks) in a COATI_GPU_TRACE=1 log: where the batch pipeline's host
+thread was blocked.  usage: python tools/trace_gaps.py gpurun_out/trace.log"""
 import re,sys
 prev=None
 for l in open(sys.argv[1]):
