@@ -6,6 +6,7 @@
 #include "../../include/coati_gpu.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -43,7 +44,7 @@ static void trace_mark(const char* what, size_t id) {
 // ---------------------------------------------------------------------------------------------
 // Grow-only device memory pool: batches borrow blocks and give them back, so repeated calls of the
 // public batch entry point do not pay cudaMalloc/cudaFree (which synchronise the device).
-static uint64_t g_alloc_epoch = 0;  // bumped by every device allocation / free made outside the pool
+static std::atomic<uint64_t> g_alloc_epoch{0};  // bumped by every device allocation / free made outside the pool
 
 struct DevPool {
     struct Block {
