@@ -968,6 +968,35 @@ int coati_host_alignment_score(const char* a, const char* b, const float* table,
     return 0;
 }
 
+// io.cc:48-88: P = expm(Q * t)^T from a "cod,cod,rate" CSV; out = 61 x 61 row-major
+int coati_host_parse_matrix_csv(const char* path, float* out) {
+    try {
+        const coati::matrix61_t P = coati::parse_matrix_csv(path);
+        std::copy(P.begin(), P.end(), out);
+    } catch(const std::invalid_argument&) {
+        return -2;
+    } catch(...) {
+        return -1;
+    }
+    return 0;
+}
+
+// read_input + write_output (io.cc:184-222, 316-346): format chosen by the extensions, as the CLI does
+int coati_host_convert(const char* in_path, const char* out_path) {
+    try {
+        coati::alignment_t aln;
+        aln.data.path = in_path;
+        aln.data = coati::read_input(aln);
+        aln.output = out_path;
+        coati::write_output(aln);
+    } catch(const std::invalid_argument&) {
+        return -2;
+    } catch(...) {
+        return -1;
+    }
+    return 0;
+}
+
 void coati_host_json_number(float v, char* out, size_t cap) {
     const std::string s = coati::json_number(v);
     std::strncpy(out, s.c_str(), cap - 1);

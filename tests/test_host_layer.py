@@ -126,3 +126,66 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([os.path.join(ROOT, "coati_b200", "bin", "coati-gpu"), "alignpair", str(fa)],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def _convert(lib, src, dst):
+    lib.coati_host_convert.argtypes = [C.c_char_p, C.c_char_p]
+    return lib.coati_host_convert(str(src).encode(), str(dst).encode())
+
+
+def test_phylip_reader_and_writers_known_answers(lib, tmp_path):
+    """read_phylip / write_phylip / write_fasta / write_json against the reference's own cases
+    (phylip.cc:101-147 interleaved input with a 10-character name field; phylip.cc:230-275 output;
+    json.cc:37-42 object layout) and a FASTA -> PHYLIP -> JSON -> FASTA round trip."""
+    src = tmp_path / "in.phy"
+    s0 = "CTCTGGATAG" * 10
+    s1 = "CTATA" * 20
+    src.write_text(" 2 100\nVeryLongNa" + s0[:60] + "\n2         " + s1[:60] + "\n\n" + s0[60:] + "\n" + s1[60:] + "\n\n")
+    assert _convert(lib, src, tmp_path / "a.fasta") == 0
+    assert (tmp_path / "a.fasta").read_text() == (">VeryLongNa\n" + s0[:60] + "\n" + s0[60:] + "\n>2\n" + s1[:60] + "\n"
+                                                   + s1[60:] + "\n")
+    assert _convert(lib, tmp_path / "a.fasta", tmp_path / "b.phy") == 0
+    lines = (tmp_path / "b.phy").read_text().split("\n")
+    assert lines[0] == "2 100"
+    assert lines[1] == "VeryLongNa" + s0[:50] and lines[2] == "2         " + s1[:50] and lines[3] == ""
+    assert lines[4] == s0[50:] and lines[5] == s1[50:]          # 60 per line after the first 50
+    assert _convert(lib, tmp_path / "b.phy", tmp_path / "c.json") == 0
+    assert (tmp_path / "c.json").read_text() == ('{\n  "alignment": {\n    "VeryLongNa": "%s",\n    "2": "%s"\n  },\n'
+                                                 '  "score": 0.0\n}\n' % (s0, s1))
+    assert _convert(lib, tmp_path / "c.json", tmp_path / "d.fa") == 0
+    assert (tmp_path / "d.fa").read_text() == (tmp_path / "a.fasta").read_text()
+    # short rows: the reference's write_phylip case
+    (tmp_path / "s.fa").write_text(">tx_1\nCTCTGGATAGTG\n>taxa_2\nCT----ATAGTG\n")
+    assert _convert(lib, tmp_path / "s.fa", tmp_path / "s.phy") == 0
+    assert (tmp_path / "s.phy").read_text().split("\n")[:3] == ["2 12", "tx_1      CTCTGGATAGTG", "taxa_2    CT----ATAGTG"]
+    # failures are exceptions upstream (io.cc:196-221): unknown extension, missing file
+    assert _convert(lib, tmp_path / "s.fa", tmp_path / "s.xyz") == -2
+    assert _convert(lib, tmp_path / "missing.fa", tmp_path / "o.fa") == -2
+
+
+def test_parse_matrix_csv_self_consistency(lib, tmp_path):
+    """--sub CSV (io.cc:48-88): expm(Q * t) of a "codon,codon,rate" file equals mg94_p built from the same
+    rates -- the reference's own test (io.cc:91-131, Approx) with Q from the oracle's builder."""
+    pi = np.array([0.308, 0.185, 0.199, 0.308], dtype=np.float32)
+    Q, d = otable.mg94_q(0.2, pi)
+    codons = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT" if a + b + c not in ("TAA", "TAG", "TGA")]
+    t = np.float32(0.0133)
+    path = tmp_path / "q.csv"
+    with open(path, "w") as fh:
+        fh.write("%.9g\n" % float(t / d))  # the file carries the normalised branch length
+        for i in range(61):
+            for j in range(61):
+                fh.write("%s,%s,%.9g\n" % (codons[i], codons[j], float(Q[i, j])))
+    lib.coati_host_parse_matrix_csv.argtypes = [C.c_char_p, _fp]
+    P = np.zeros(61 * 61, dtype=np.float32)
+    assert lib.coati_host_parse_matrix_csv(str(path).encode(), P.ctypes.data_as(_fp)) == 0
+    want = np.zeros(61 * 61, dtype=np.float32)
+    sigma = np.zeros(6, dtype=np.float32)
+    assert lib.coati_host_mg94_p(C.c_float(0.0133), C.c_float(0.2), pi.ctypes.data_as(_fp), sigma.ctypes.data_as(_fp),
+                                 want.ctypes.data_as(_fp)) == 0
+    assert np.allclose(P, want, rtol=2e-5, atol=1e-7)
+    # wrong line count / unreadable file -> invalid_argument upstream
+    with open(path, "a") as fh:
+        fh.write("AAA,AAA,0\n")
+    assert lib.coati_host_parse_matrix_csv(str(path).encode(), P.ctypes.data_as(_fp)) == -2
+    assert lib.coati_host_parse_matrix_csv(b"", P.ctypes.data_as(_fp)) == -2
