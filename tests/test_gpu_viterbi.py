@@ -335,3 +335,53 @@ def test_pipelined_lanes_equal_single_call(nsub, tables):
         assert (rows_a[p], rows_b[p]) == (oa, ob) and util.f32_bits(score[p]) == util.f32_bits(osc), p
     assert sorted(outs[1][2][3])[:3] == [-7, -6, -5]
     ctx.close()
+
+
+@pytest.mark.parametrize("workload,k,tname,n", [(5, 1, "mg_c5", 200000), (4, 3, "ecm_default", 20000)])
+def test_workload_scale_properties(workload, k, tname, n, tables):
+    """BASELINE configs[4] / configs[3] shapes at bench scale (a fifth of the pair count by default,
+    COATI_TEST_PAIRS overrides): size-independent properties of EVERY alignment (tests/util.check_batch_properties:
+    rows strip to the inputs, no gap-gap column, lengths, terminators), oracle equality on a sample and on the
+    largest lattices, and identical results from the three entry points (staged batch, pipelined CSR call,
+    raw-sequence call)."""
+    import coati_b200
+    from coati_b200 import capi
+    from coati_b200.capi import synth_pairs
+    n = int(os.environ.get("COATI_TEST_PAIRS", n))
+    g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
+    T = tables[tname]
+    w = synth_pairs(n, workload, 42)
+    total = int(w["a_off"][-1] + w["b_off"][-1]) + n
+
+    def buffers():
+        return (np.zeros(total + 1, np.uint8), np.zeros(total + 1, np.uint8), np.zeros(n, np.uint64),
+                np.zeros(n, np.float32), np.zeros(n, np.int32))
+
+    ctx = coati_b200.Context(0)
+    ctx.set_model(T, g, e, k)
+    # (1) staged batch API (what bench.py times as `value`)
+    oa1, ob1, ln1, sc1, st1 = buffers()
+    bt = ctx.batch(w["a_off"], w["b_off"])
+    bt.upload(w["a_all"], w["b_all"], w["anc_all"], w["des_all"])
+    bt.run()
+    bt.download(oa1, ob1, ln1, sc1, st1)
+    bt.destroy()
+    assert util.check_batch_properties(w, oa1, ob1, ln1, sc1, st1, T, k, g, e, oracle) >= 4
+    # (2) the pipelined public call on the same encoded input
+    oa2, ob2, ln2, sc2, st2 = buffers()
+    ctx._check(ctx.lib.coati_gpu_viterbi_batch(
+        ctx.h, n, w["a_all"].ctypes.data, w["a_off"].ctypes.data_as(capi._u64p), w["b_all"].ctypes.data,
+        w["b_off"].ctypes.data_as(capi._u64p), w["anc_all"].ctypes.data, w["des_all"].ctypes.data,
+        oa2.ctypes.data, ob2.ctypes.data, ln2.ctypes.data_as(capi._u64p), sc2.ctypes.data_as(capi._fp),
+        st2.ctypes.data_as(capi._i32p)))
+    util.check_batch_properties(w, oa2, ob2, ln2, sc2, st2, T, k, g, e, oracle, exact=False)
+    # (3) the raw-sequence call (what bench.py times as `e2e`); the generator's ancestors are stop-free, a
+    # mutated descendant may end in a stop codon, which this entry point trims and restores
+    oa3, ob3, ln3, sc3, st3 = buffers()
+    ctx._check(ctx.lib.coati_gpu_alignpair_batch(
+        ctx.h, n, w["anc_all"].ctypes.data, w["a_off"].ctypes.data_as(capi._u64p), w["des_all"].ctypes.data,
+        w["b_off"].ctypes.data_as(capi._u64p), oa3.ctypes.data, ob3.ctypes.data, ln3.ctypes.data_as(capi._u64p),
+        sc3.ctypes.data_as(capi._fp), st3.ctypes.data_as(capi._i32p)))
+    util.check_batch_properties(w, oa3, ob3, ln3, sc3, st3, T, k, g, e, oracle, exact=False)
+    util.compare_entry_points(w, (oa1, ob1, ln1, sc1, st1), (oa2, ob2, ln2, sc2, st2), (oa3, ob3, ln3, sc3, st3))
+    ctx.close()

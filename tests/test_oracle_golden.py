@@ -181,3 +181,95 @@ def test_gtr_q_golden():
     np.testing.assert_allclose(q, exp, rtol=2e-5, atol=1e-8)
     with pytest.raises(ValueError):
         otable.gtr_q((0.25,) * 4, (-0.1, 0, 0, 0, 0, 0))
+
+
+def test_batch_property_checker_on_oracle_output(tables):
+    """The vectorised property checker the GPU tests run at workload scale (tests/util.check_batch_properties),
+    exercised here on arenas filled by the oracle -- and on deliberately corrupted arenas, which it must reject."""
+    from coati_b200.capi import synth_pairs
+    g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
+    for workload, k, tname in ((5, 1, "mg_c5"), (4, 3, "ecm_default")):
+        w = synth_pairs(24 if workload == 5 else 6, workload, 42, threads=1)
+        T = tables[tname]
+        a_off, b_off = w["a_off"].astype(np.int64), w["b_off"].astype(np.int64)
+        n = len(a_off) - 1
+        total = int(a_off[-1] + b_off[-1]) + n
+        out_a, out_b = np.zeros(total + 1, np.uint8), np.zeros(total + 1, np.uint8)
+        out_len, score, status = np.zeros(n, np.uint64), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        for p in range(n):
+            anc = w["anc_all"][a_off[p]:a_off[p + 1]].tobytes().decode()
+            des = w["des_all"][b_off[p]:b_off[p + 1]].tobytes().decode()
+            ra, rb, sc = oracle.viterbi(anc, des, T, g, e, k,
+                                        enc=(w["a_all"][a_off[p]:a_off[p + 1]], w["b_all"][b_off[p]:b_off[p + 1]]))
+            o = int(a_off[p] + b_off[p]) + p
+            out_a[o:o + len(ra)] = np.frombuffer(ra.encode(), np.uint8)
+            out_b[o:o + len(rb)] = np.frombuffer(rb.encode(), np.uint8)
+            out_len[p], score[p] = len(ra), sc
+        assert util.check_batch_properties(w, out_a, out_b, out_len, score, status, T, k, g, e, oracle, sample=8) >= 4
+        # corruptions: a flipped symbol, a wrong score, a failed pair, a missing terminator
+        o3 = int(a_off[3] + b_off[3]) + 3
+        for mutate in ("symbol", "score", "status", "nul"):
+            ca, cs, st = out_a.copy(), score.copy(), status.copy()
+            if mutate == "symbol":
+                j = o3 + int(np.flatnonzero(ca[o3:o3 + int(out_len[3])] != ord("-"))[0])
+                ca[j] = ord("A") if ca[j] != ord("A") else ord("C")
+            elif mutate == "score":
+                cs[:] = cs + np.float32(1.0)
+            elif mutate == "status":
+                st[5] = -5
+            else:
+                ca[o3 + int(out_len[3])] = ord("A")
+            with pytest.raises(AssertionError):
+                util.check_batch_properties(w, ca, out_b, out_len, cs, st, T, k, g, e, oracle, sample=n * 4)
+
+
+def test_entry_point_comparison_on_oracle_output(tables):
+    """tests/util.compare_entry_points (used by the GPU workload-scale test) on arenas made by the oracle the
+    way the three entry points fill them: scratch bytes after the terminators differ, and the raw-sequence
+    call trims and restores end stops (two descendants are made to end in a stop codon)."""
+    from coati_b200.capi import synth_pairs
+    g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
+    T = tables["mg_c5"]
+    w = synth_pairs(20, 5, 42, threads=1)
+    a_off, b_off = w["a_off"].astype(np.int64), w["b_off"].astype(np.int64)
+    for p in (2, 7):  # ...TAA at the end of two descendants (IUPAC codes T = 3, A = 0)
+        w["des_all"][b_off[p + 1] - 3:b_off[p + 1]] = np.frombuffer(b"TAA", np.uint8)
+        w["b_all"][b_off[p + 1] - 3:b_off[p + 1]] = (3, 0, 0)
+    n = 20
+    total = int(a_off[-1] + b_off[-1]) + n
+    rng = np.random.RandomState(3)
+
+    def fill(raw):
+        oa = rng.randint(1, 255, total + 1).astype(np.uint8)  # scratch everywhere, rows written over it
+        ob = rng.randint(1, 255, total + 1).astype(np.uint8)
+        ln, sc, st = np.zeros(n, np.uint64), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        for p in range(n):
+            anc = w["anc_all"][a_off[p]:a_off[p + 1]].tobytes().decode()
+            des = w["des_all"][b_off[p]:b_off[p + 1]].tobytes().decode()
+            if raw:
+                at, s0 = oracle.trim_end_stop(anc)
+                dt, s1 = oracle.trim_end_stop(des)
+                ra, rb, x = oracle.viterbi(at, dt, T, g, e, 1)
+                ra, rb, x = oracle.restore_end_stops(ra, rb, x, (s0, s1), g, e)
+            else:
+                ra, rb, x = oracle.viterbi(anc, des, T, g, e, 1)
+            o = int(a_off[p] + b_off[p]) + p
+            oa[o:o + len(ra)] = np.frombuffer(ra.encode(), np.uint8)
+            ob[o:o + len(rb)] = np.frombuffer(rb.encode(), np.uint8)
+            oa[o + len(ra)] = ob[o + len(rb)] = 0
+            ln[p], sc[p] = len(ra), x
+        return oa, ob, ln, sc, st
+
+    staged, piped, raw = fill(False), fill(False), fill(True)
+    for r, exact in ((staged, True), (piped, False), (raw, False)):
+        util.check_batch_properties(w, *r, T, 1, g, e, oracle, sample=6, exact=exact)
+    assert util.compare_entry_points(w, staged, piped, raw) == 2
+    bad = tuple(x.copy() for x in piped)
+    bad[3][4] += np.float32(0.5)
+    with pytest.raises(AssertionError):
+        util.compare_entry_points(w, staged, bad, raw)
+    bad = tuple(x.copy() for x in raw)
+    o = int(a_off[9] + b_off[9]) + 9
+    bad[1][o] = ord("-") if bad[1][o] != ord("-") else ord("A")
+    with pytest.raises(AssertionError):
+        util.compare_entry_points(w, staged, piped, bad)
