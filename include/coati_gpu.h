@@ -120,8 +120,10 @@ int coati_gpu_batch_download(coati_gpu_batch* batch, char* out_a, char* out_b, u
 /* counters of the last run: lattice cells filled, direction bytes written, kernels launched */
 int coati_gpu_batch_stats(coati_gpu_batch* batch, uint64_t* cells, uint64_t* dir_bytes,
                           uint64_t* launches, uint64_t* chunks);
-/* device time of the last run split by kernel family, from CUDA events recorded on the context's
- * stream around each launch (synchronises the stream); fill_launches = fill kernels launched */
+/* device time of the last run split by kernel family, from CUDA events recorded on the batch's
+ * streams (synchronises them): fill = every fill launch; traceback = the walks of each chunk (for long
+ * pairs including their segment-parallel row expansion); compact = the row expansion of each chunk;
+ * fill_launches = fill kernels launched */
 int coati_gpu_batch_timing(coati_gpu_batch* batch, double* fill_ms, double* traceback_ms,
                            double* compact_ms, uint64_t* fill_launches);
 /* device-resident outputs of the last run (for a NCCL gather of per-rank results): the two row
