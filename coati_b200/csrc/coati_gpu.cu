@@ -44,8 +44,6 @@ static void trace_mark(const char* what, size_t id) {
 // ---------------------------------------------------------------------------------------------
 // Grow-only device memory pool: batches borrow blocks and give them back, so repeated calls of the
 // public batch entry point do not pay cudaMalloc/cudaFree (which synchronise the device).
-static std::atomic<uint64_t> g_alloc_epoch{0};  // bumped by every device allocation / free made outside the pool
-
 struct DevPool {
     struct Block {
         void* p;
@@ -53,7 +51,6 @@ struct DevPool {
         bool used;
     };
     std::vector<Block> blocks;
-    uint64_t generation = 0;  // bumped by every cudaMalloc / cudaFree of the pool
     void* take(size_t bytes, cudaError_t* err) {
         *err = cudaSuccess;
         if(bytes == 0) return nullptr;
@@ -82,7 +79,6 @@ struct DevPool {
             if(*err != cudaSuccess) return nullptr;
         }
         blocks.push_back(Block{p, padded, true});
-        ++generation;
         return p;
     }
     void give(void* p) {
@@ -90,7 +86,6 @@ struct DevPool {
             if(b.p == p) b.used = false;
     }
     void trim() {
-        ++generation;
         for(size_t i = 0; i < blocks.size();) {
             if(!blocks[i].used) {
                 cudaFree(blocks[i].p);
@@ -165,21 +160,18 @@ struct coati_gpu_ctx {
     bool tb_serial = false;  // COATI_GPU_TB_SERIAL=1: long pairs walked one column at a time (A/B)
     uint32_t force_r = 0;  // COATI_GPU_FORCE_R: rows per lane of every inter-pair fill (tuning)
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
+    bool sample_serial = false;  // COATI_GPU_SAMPLE_SERIAL=1: one thread draws all samples (A/B)
+    bool pipe_scalar = false;  // COATI_GPU_PIPE_SCALAR=1: scalar template instead of the FADD2 kernels (A/B)
+    int ctas_per_sm[32] = {};  // per entry of the kernel registry, on this device
+    uint64_t model_gen = 0;    // bumped by every coati_gpu_set_model(s): Forward handles remember theirs
     DevPool pool;
     HostPool hpool;
-    // cudaMemGetInfo costs tens of ms on a device with a lot of memory mapped: ask again only when the
-    // pool has allocated or freed since the last answer
-    size_t cached_free = 0;
-    uint64_t cached_free_gen = ~0ull;
+    // Free device memory, asked afresh by every top-level batch call before its first kernel (other
+    // libraries and processes allocate on the same device; a cached answer goes stale).  Never called
+    // inside the sub-batch pipeline: cudaMemGetInfo can block for tens of ms beside running kernels.
     cudaError_t free_bytes(size_t* out) {
-        if(cached_free_gen != pool.generation + g_alloc_epoch) {
-            size_t total_b = 0;
-            cudaError_t e = cudaMemGetInfo(&cached_free, &total_b);
-            if(e != cudaSuccess) return e;
-            cached_free_gen = pool.generation + g_alloc_epoch;
-        }
-        *out = cached_free;
-        return cudaSuccess;
+        size_t total_b = 0;
+        return cudaMemGetInfo(out, &total_b);
     }
 };
 
@@ -210,16 +202,12 @@ struct DevBuf {
             p = static_cast<T*>(pool->take(count * sizeof(T), &e));
             return e;
         }
-        ++g_alloc_epoch;
         return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
     }
     void release() {
         if(p) {
             if(pool) pool->give(p);
-            else {
-                cudaFree(p);
-                ++g_alloc_epoch;
-            }
+            else cudaFree(p);
         }
         p = nullptr;
         n = 0;
@@ -247,47 +235,65 @@ typedef void (*pipe_kernel_t)(const PairDesc*, uint32_t, uint32_t, unsigned int*
                               PairResult*);
 typedef void (*pipe1_kernel_t)(const PairDesc*, uint32_t, uint32_t, unsigned int*, const uint8_t*,
                                const uint8_t*, const float*, GapConsts, float4*, uint32_t, uint8_t*,
-                               PairResult*, uint32_t*);
+                               PairResult*, const unsigned int*);
 struct PipeCfg {
     uint32_t k, R;
     bool wave;
     uint32_t nc;  // substitution columns held per lane (16, or 4 for ACGT-only descendants)
+    bool ab;      // A/B form, only eligible under COATI_GPU_PIPE_SCALAR=1 (scalar template in place of FADD2)
     pipe_kernel_t fn;    // generic-K pipelined kernel (viterbi_pipe.cuh)
-    pipe1_kernel_t fn1;  // K = 1 specialisation (viterbi_pipe1.cuh); takes precedence when set
+    pipe1_kernel_t fn1;  // FADD2 specialisations (viterbi_pipe1.cuh, viterbi_pipe3.cuh); takes precedence
     size_t smem;
-    int ctas_per_sm;
     const void* entry() const { return fn1 ? (const void*)fn1 : (const void*)fn; }
 };
 template <int K, int R>
-PipeCfg make_cfg() {
-    return PipeCfg{(uint32_t)K, (uint32_t)R, false, 16, viterbi_pipe_kernel<K, R>, nullptr,
-                   (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4), 0};
+PipeCfg make_cfg(bool ab) {
+    return PipeCfg{(uint32_t)K, (uint32_t)R, false, 16, ab, viterbi_pipe_kernel<K, R>, nullptr,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * 16 * 32 * sizeof(float4)};
 }
 template <int R, bool WAVE, int NC>
 PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false) or intra-pair wavefront
-    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, nullptr, viterbi_pipe1_kernel<R, WAVE, NC, true>,
-                   (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
+    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, false, nullptr, viterbi_pipe1_kernel<R, WAVE, NC>,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4)};
 }
 template <int R, int NC>
 PipeCfg make_cfg3() {  // K = 3: FADD2 specialisation (viterbi_pipe3.cuh)
-    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, nullptr, viterbi_pipe3_kernel<R, NC>,
-                   (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4), 0};
+    return PipeCfg{3u, (uint32_t)R, false, (uint32_t)NC, false, nullptr, viterbi_pipe3_kernel<R, NC>,
+                   (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4)};
 }
-PipeCfg g_pipe_cfgs[] = {make_cfg1<4, false, 16>(), make_cfg1<8, false, 16>(), make_cfg<3, 3>(),
-                         make_cfg3<6, 16>(),        make_cfg1<2, true, 16>(),  make_cfg1<4, true, 16>(),
-                         make_cfg1<8, true, 16>(),  make_cfg1<4, false, 4>(),  make_cfg1<8, false, 4>(),
-                         make_cfg1<8, true, 4>(),   make_cfg3<6, 4>(),         make_cfg1<10, false, 16>(),
-                         make_cfg1<10, false, 4>(), make_cfg1<10, true, 16>(),  make_cfg1<10, true, 4>()};
+// Immutable after static initialisation (contexts on several host threads read it concurrently); what
+// depends on the device -- resident CTAs per SM -- lives in the context.
+const PipeCfg g_pipe_cfgs[] = {
+    make_cfg1<4, false, 16>(), make_cfg1<4, false, 4>(),  make_cfg1<8, false, 16>(), make_cfg1<8, false, 4>(),
+    make_cfg1<10, false, 16>(), make_cfg1<10, false, 4>(), make_cfg<3, 3>(false),    make_cfg3<6, 16>(),
+    make_cfg3<6, 4>(),         make_cfg1<2, true, 16>(),  make_cfg1<2, true, 4>(),   make_cfg1<4, true, 16>(),
+    make_cfg1<4, true, 4>(),   make_cfg1<8, true, 16>(),  make_cfg1<8, true, 4>(),   make_cfg1<10, true, 16>(),
+    make_cfg1<10, true, 4>(),
+    // A/B: the scalar template where a FADD2 specialisation exists
+    make_cfg<1, 4>(true),      make_cfg<1, 8>(true),      make_cfg<3, 6>(true)};
+constexpr int N_PIPE_CFG = (int)(sizeof(g_pipe_cfgs) / sizeof(g_pipe_cfgs[0]));
 
+// configurations the planner may pick for inter-pair fills: the specialisations, or (A/B run) only the
+// scalar template's instances
+bool cfg_eligible(const PipeCfg& pc, bool scalar_ab) {
+    return scalar_ab ? (pc.fn != nullptr && pc.fn1 == nullptr) : !pc.ab;
+}
 // nc = 4 picks the ACGT-only variant when it exists, else falls back to the 16-column kernel
-const PipeCfg* find_cfg(uint32_t k, uint32_t cfg, uint32_t nc = 16) {
+const PipeCfg* find_cfg(uint32_t k, uint32_t cfg, uint32_t nc, bool scalar_ab) {
     const PipeCfg* fallback = nullptr;
     for(const PipeCfg& pc : g_pipe_cfgs)
-        if(pc.k == k && pc.R == (cfg & 0xffu) && pc.wave == ((cfg & CFG_WAVE) != 0)) {
+        if(pc.k == k && pc.R == (cfg & 0xffu) && pc.wave == ((cfg & CFG_WAVE) != 0) &&
+           (pc.wave || cfg_eligible(pc, scalar_ab))) {
             if(pc.nc == nc) return &pc;
             if(pc.nc == 16) fallback = &pc;
         }
     return fallback;
+}
+
+// float4 entries of the wavefront's boundary rows: (bands + 1) rows of (lb + 4) / 2 float4 = lb + 4 float2
+uint64_t wave_bnd_f4(uint32_t la, uint32_t lb, uint32_t R) {
+    const uint64_t nb = (la + 32 * R - 1) / (32 * R);
+    return (nb + 1) * ((lb + 4) / 2);
 }
 
 // issue-slot model of one pair on one warp: bands x steps x instructions per step (SASS counts of the
@@ -395,25 +401,8 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
         ctx->dir_budget = static_cast<size_t>(std::strtoull(env, nullptr, 10)) << 20;
     }
     if(const char* env = std::getenv("COATI_GPU_FORCE_GENERIC")) ctx->force_generic = env[0] == '1';
-    if(const char* env = std::getenv("COATI_GPU_PIPE_SCALAR")) {  // A/B: scalar template for K = 1
-        if(env[0] == '1') {
-            g_pipe_cfgs[0].fn = viterbi_pipe_kernel<1, 4>, g_pipe_cfgs[0].fn1 = nullptr;
-            g_pipe_cfgs[1].fn = viterbi_pipe_kernel<1, 8>, g_pipe_cfgs[1].fn1 = nullptr;
-            g_pipe_cfgs[3].fn = viterbi_pipe_kernel<3, 6>, g_pipe_cfgs[3].fn1 = nullptr;
-            g_pipe_cfgs[3].smem = (size_t)PIPE_WARPS * 2 * 16 * 32 * sizeof(float4);
-            g_pipe_cfgs[10].k = 0;  // disable the ACGT-only K = 3 variant as well
-        }
-    }
-    if(const char* env = std::getenv("COATI_GPU_PIPE_SGN")) {  // A/B: FSETP + IMAD decisions for K = 1
-        if(env[0] == '0') {
-            g_pipe_cfgs[0].fn1 = viterbi_pipe1_kernel<4, false, 16, false>;
-            g_pipe_cfgs[1].fn1 = viterbi_pipe1_kernel<8, false, 16, false>;
-            g_pipe_cfgs[7].fn1 = viterbi_pipe1_kernel<4, false, 4, false>;
-            g_pipe_cfgs[8].fn1 = viterbi_pipe1_kernel<8, false, 4, false>;
-            g_pipe_cfgs[5].fn1 = viterbi_pipe1_kernel<4, true, 16, false>;
-            g_pipe_cfgs[6].fn1 = viterbi_pipe1_kernel<8, true, 16, false>;
-        }
-    }
+    if(const char* env = std::getenv("COATI_GPU_PIPE_SCALAR")) ctx->pipe_scalar = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_SAMPLE_SERIAL")) ctx->sample_serial = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_TB_SERIAL")) ctx->tb_serial = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_FORCE_R")) ctx->force_r = (uint32_t)std::atoi(env);
@@ -421,12 +410,14 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
         const uint32_t r = (uint32_t)std::atoi(env);
         if(r == 2 || r == 4 || r == 8 || r == 10) ctx->wave_r = r;
     }
-    for(PipeCfg& pc : g_pipe_cfgs) {
+    static_assert(N_PIPE_CFG <= 32, "ctx->ctas_per_sm");
+    for(int x = 0; x < N_PIPE_CFG; ++x) {  // function attributes are per device: set for this one
+        const PipeCfg& pc = g_pipe_cfgs[x];
         if(cudaFuncSetAttribute(pc.entry(), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)pc.smem) != cudaSuccess ||
-           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pc.ctas_per_sm, pc.entry(),
+           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->ctas_per_sm[x], pc.entry(),
                                                          PIPE_WARPS * 32, pc.smem) != cudaSuccess ||
-           pc.ctas_per_sm < 1) {
+           ctx->ctas_per_sm[x] < 1) {
             cudaGetLastError();
             coati_gpu_shutdown(ctx);
             return COATI_GPU_E_CUDA;
@@ -515,6 +506,7 @@ extern "C" int coati_gpu_set_models(coati_gpu_ctx* ctx, uint32_t n_models, const
     ctx->gap = c;
     ctx->n_models = n_models;
     ctx->model_set = true;
+    ++ctx->model_gen;
     return COATI_GPU_OK;
 }
 
@@ -605,7 +597,9 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
         if(!ctx->force_generic && la > 0 && lb > 0) {
             double best = 0;
             for(const PipeCfg& pc : g_pipe_cfgs) {
-                if(pc.k != k || pc.wave || (ctx->force_r && pc.R != ctx->force_r)) continue;
+                if(pc.k != k || pc.wave || !cfg_eligible(pc, ctx->pipe_scalar) ||
+                   (ctx->force_r && pc.R != ctx->force_r))
+                    continue;
                 const double c = pipe_cost(d.la, d.lb, pc.R);
                 if(d.cfg == 0 || c < best) best = c, d.cfg = pc.R;
             }
@@ -714,18 +708,18 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
     uint32_t wave_bands = 0;
     for(const Run& r : bt->runs) {
         if(!r.cfg) continue;
-        const PipeCfg* pc = find_cfg(k, r.cfg);
+        const PipeCfg* pc = find_cfg(k, r.cfg, 16, ctx->pipe_scalar);
         if(!pc) return COATI_GPU_E_ARG;
         if(r.cfg & CFG_WAVE) {
             const PairDesc& d = bt->descs[r.first];
             const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
             wave_bands = std::max(wave_bands, nb);
-            wave_f4 = std::max<uint64_t>(wave_f4, (uint64_t)(nb + 1) * ((d.lb + 4) / 2));
+            wave_f4 = std::max<uint64_t>(wave_f4, wave_bnd_f4(d.la, d.lb, pc->R));
         } else {
             const uint32_t want = (r.last - r.first + PIPE_WARPS - 1) / PIPE_WARPS;
-            const PipeCfg* pc4 = find_cfg(k, r.cfg, 4);  // ACGT-only variant may be more resident
+            const PipeCfg* pc4 = find_cfg(k, r.cfg, 4, ctx->pipe_scalar);  // ACGT-only variant may be more resident
             const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount *
-                                 std::max(pc->ctas_per_sm, pc4 ? pc4->ctas_per_sm : 0);
+                                 std::max(ctx->ctas_per_sm[pc - g_pipe_cfgs], ctx->ctas_per_sm[pc4 - g_pipe_cfgs]);
             bt->bnd_ctas = std::max(bt->bnd_ctas, std::min(want, cap));
         }
     }
@@ -871,12 +865,8 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
             encode_pairs_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
                                   s>>>(bt->d_pairs.p, n, bt->d_anc.p, bt->d_des.p, bt->d_a.p, bt->d_b.p,
                                        bt->d_results.p, flag);
-            unsigned int h_flag = 1;
             trace_mark("  run: encode enqueued", n);
-            CU_TRY(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
-            CU_TRY(ctx, cudaStreamSynchronize(s));  // only this sub-batch's H2D + encode are waited on
-            trace_mark("  run: encode done", n);
-            bt->nc = h_flag ? 16 : 4;
+            bt->nc = 16;  // decided on the device: see the fill launches below
         } else
             validate_symbols_kernel<<<(n + warps_per_block - 1) / warps_per_block,
                                       warps_per_block * 32, 0, s>>>(bt->d_pairs.p, n, bt->d_a.p,
@@ -921,34 +911,47 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                             bt->d_results.p);
                 any_inter = true;
             } else {
-                const PipeCfg* pc = find_cfg(ctx->gap.k, r.cfg, bt->nc);
-                if(!pc) return COATI_GPU_E_ARG;
-                const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * pc->ctas_per_sm;
-                if(pc->wave) {
-                    const PairDesc& d = bt->descs[r.first];
-                    const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
-                    const uint32_t grid = std::min((nb + PIPE_WARPS - 1) / PIPE_WARPS, cap);
-                    // NaN sentinel in every boundary entry: the data is its own ready flag
-                    CU_TRY(ctx, cudaMemsetAsync(bt->d_bnd.p, 0xff,
-                                                (size_t)(nb + 1) * ((d.lb + 4) / 2) * sizeof(float4), sf));
-                    pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
-                        bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                        ctx->d_table, ctx->gap, bt->d_bnd.p, (d.lb + 4) / 2, bt->d_dirs.p,
-                        bt->d_results.p, bt->d_prog.p);
-                } else {
-                    const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
-                    const uint32_t grid = std::min(want, std::min(bt->bnd_ctas, cap));
-                    if(pc->fn1)
+                const PipeCfg* pc16 = find_cfg(ctx->gap.k, r.cfg, 16, ctx->pipe_scalar);
+                const PipeCfg* pc4 = find_cfg(ctx->gap.k, r.cfg, 4, ctx->pipe_scalar);
+                if(!pc16) return COATI_GPU_E_ARG;
+                // Raw-sequence batches learn on the device whether any descendant carries an ambiguity code
+                // (encode_pairs_kernel sets a flag word): both column variants are launched and the one
+                // that does not apply returns at once, so the host never synchronises on the flag.
+                const PipeCfg* todo[2] = {bt->nc == 4 ? pc4 : pc16, nullptr};
+                const unsigned int* nc_flag = nullptr;
+                if(bt->raw && pc4 != pc16 && pc16->fn1) {
+                    todo[0] = pc16, todo[1] = pc4;
+                    nc_flag = bt->d_counters.p + bt->runs.size();
+                }
+                const PairDesc& d = bt->descs[r.first];
+                if(pc16->wave)  // NaN sentinel in every boundary entry: the data is its own ready flag
+                    CU_TRY(ctx, cudaMemsetAsync(bt->d_bnd.p, 0xff, wave_bnd_f4(d.la, d.lb, pc16->R) * sizeof(float4), sf));
+                for(const PipeCfg* pc : todo) {
+                    if(!pc) continue;
+                    const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * ctx->ctas_per_sm[pc - g_pipe_cfgs];
+                    if(pc->wave) {
+                        const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
+                        const uint32_t grid = std::min((nb + PIPE_WARPS - 1) / PIPE_WARPS, cap);
                         pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
                             bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                            ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
-                            bt->d_results.p, nullptr);
-                    else
-                        pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
-                            bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
-                            ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
-                            bt->d_results.p);
-                    any_inter = true;
+                            ctx->d_table, ctx->gap, bt->d_bnd.p, (d.lb + 4) / 2, bt->d_dirs.p,
+                            bt->d_results.p, nc_flag);
+                    } else {
+                        const uint32_t want = (cnt + PIPE_WARPS - 1) / PIPE_WARPS;
+                        const uint32_t grid = std::min(want, std::min(bt->bnd_ctas, cap));
+                        if(pc->fn1)
+                            pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
+                                bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                                ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
+                                bt->d_results.p, nc_flag);
+                        else
+                            pc->fn<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
+                                bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,
+                                ctx->d_table, ctx->gap, bt->d_bnd.p, bt->bnd_stride, bt->d_dirs.p,
+                                bt->d_results.p);
+                        any_inter = true;
+                    }
+                    if(pc != todo[0]) ++bt->launches;
                 }
             }
             cudaEventRecord(ev[1], sf);
@@ -1156,8 +1159,12 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
     if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
     int rc = viterbi_batch_pipeline(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
                                     out_len, score, status, raw_mode, model, nsub);
-    if(rc == COATI_GPU_E_NOMEM && nsub > 1) {
-        // a lane owns a third of the memory: a pair too big for that still fits the whole device
+    if(rc == COATI_GPU_E_NOMEM) {
+        // a lane owns a third of the memory: a pair too big for that may still fit the whole device; and
+        // idle pool blocks of earlier calls are given back before the plan is redone from the memory
+        // that is free now
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        CU_TRY(ctx, cudaDeviceSynchronize());
         ctx->pool.trim();
         rc = viterbi_batch_pipeline(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
                                     out_len, score, status, raw_mode, model, 1);
@@ -1382,6 +1389,7 @@ struct coati_gpu_forward_t {
     DevBuf<uint32_t> d_draws;
     DevBuf<uint64_t> d_starts, d_cursor;
     bool rec_ready = false;
+    uint64_t model_gen = 0;  // the context's model when the matrices were filled
     float term[3] = {0, 0, 0};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float fill_ms = 0, sample_ms = 0;
@@ -1405,6 +1413,7 @@ extern "C" int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La
     std::unique_ptr<coati_gpu_forward_t> h(new(std::nothrow) coati_gpu_forward_t);
     if(!h) return COATI_GPU_E_NOMEM;
     h->ctx = ctx;
+    h->model_gen = ctx->model_gen;
     h->la = (uint32_t)La;
     h->lb = (uint32_t)Lb;
     const uint64_t plane = (uint64_t)(La + 1) * (Lb + 1);
@@ -1468,6 +1477,9 @@ extern "C" int coati_gpu_sampleback(coati_gpu_forward_t* h, const char* anc, con
     if(!h || !rng_state || (n && (!out_a || !out_b))) return COATI_GPU_E_ARG;
     if((h->la && !anc) || (h->lb && !des) || n > 0x7fffffffull) return COATI_GPU_E_ARG;
     coati_gpu_ctx* ctx = h->ctx;
+    // the matrices belong to the model they were filled under: sampling them with another table or other
+    // gap constants would be silently wrong
+    if(h->model_gen != ctx->model_gen) return COATI_GPU_E_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const size_t stride = (size_t)h->la + h->lb + 1;
@@ -1492,11 +1504,7 @@ extern "C" int coati_gpu_sampleback(coati_gpu_forward_t* h, const char* anc, con
     }
     const uint64_t zero = 0;
     const uint64_t st[2] = {rng_state[0] | 1ull, rng_state[1]};  // Lehmer64Fast::SetState (random.hpp:131-134)
-    static const bool serial_env = [] {
-        const char* e = std::getenv("COATI_GPU_SAMPLE_SERIAL");
-        return e && e[0] == '1';
-    }();
-    if(n >= 4 && !serial_env) {
+    if(n >= 4 && !ctx->sample_serial) {
         // ---- parallel path: records -> speculative draw counts -> chase -> parallel re-walk ----------
         const uint64_t ncells = (uint64_t)(h->la + 1) * (h->lb + 1);
         const uint64_t max_draws = (uint64_t)h->la + h->lb + 1;

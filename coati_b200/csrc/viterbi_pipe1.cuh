@@ -4,9 +4,9 @@
 //   * the match/insert halves of two adjacent rows are evaluated with packed add.rn.f32x2 (FADD2); each
 //     lane of a packed add is an IEEE round-to-nearest FADD, so results are bit-identical to the scalar
 //     form;
-//   * decisions (SGN form, the default) are the sign bits of five packed subtractions per row pair,
-//     pushed into the plane accumulators by funnel shifts: 1.5 instructions per decision bit; the
-//     FSETP + predicated IMAD form (2 per bit) is kept as SGN = false for A/B runs;
+//   * decisions are the sign bits of five packed subtractions per row pair, pushed into the plane
+//     accumulators by funnel shifts: 1.5 instructions per decision bit (an FSETP + predicated IMAD
+//     form, 2 per bit, was measured in round 1 and removed: profiles/r01_pipe1_fadd2_imad_ncu.txt);
 //   * the symbol, the row above the band and the row below it move on uniform addresses
 //     (lane 31 carries lane 0's inputs in its outgoing shuffle registers), so the per-step
 //     overhead is three shuffles, two broadcast loads and one predicated store;
@@ -52,35 +52,7 @@ __device__ __forceinline__ void push_sign(uint32_t& acc, float d) {
     acc = __funnelshift_l(__float_as_uint(d), acc, 1);
 }
 
-// acc |= bm when a == b / a > b, as FSETP + predicated LOP3 (the compiler's own lowering of
-// `if(a == b) acc |= bm` is FSETP + SEL + LOP3)
-// The OR is issued as a predicated IMAD (acc += bm * one; the bit is never set twice), because the
-// ALU pipe (FSETP, FMNMX, LOP3: half rate) is the binding pipe of this kernel and the FMA pipe is not.
-__device__ __forceinline__ void or_if_eq(uint32_t& acc, float a, float b, uint32_t bm, uint32_t one) {
-    asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "f"(a), "f"(b), "r"(bm), "r"(one));
-}
-__device__ __forceinline__ void or_if_gt(uint32_t& acc, float a, float b, uint32_t bm, uint32_t one) {
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "f"(a), "f"(b), "r"(bm), "r"(one));
-}
-
-// one row of the column: scalar D-part, maxima, decisions (align_pair.cc:97-124, 275-296)
-#define COATI_ROW(q, xmq, ymq, zmq, xiq, yiq, ziq)                                           \
-    {                                                                                        \
-        const float xd = D + g.gs, yd = D + g.ge;                                            \
-        const float X = fmaxf(fmaxf(xmq, xd), xiq);                                          \
-        const float Y = fmaxf(fmaxf(ymq, yd), yiq);                                          \
-        const float Z = fmaxf(zmq, ziq);                                                     \
-        or_if_eq(acc[q][0], xmq, X, bm, one);                                                \
-        or_if_eq(acc[q][1], xd, X, bm, one);                                                 \
-        or_if_eq(acc[q][2], ymq, Y, bm, one);                                                \
-        or_if_eq(acc[q][3], yd, Y, bm, one);                                                 \
-        or_if_gt(acc[q][4], zmq, ziq, bm, one);                                              \
-        Xp[q] = X;                                                                           \
-        Zp[q] = Z;                                                                           \
-        D = Y;                                                                               \
-    }
-
-// Sign-shift form of a row PAIR (SGN kernels): the five decisions of both rows are the sign bits of
+// Sign-shift form of a row PAIR: the five decisions of both rows are the sign bits of
 // five packed subtractions, pushed into the plane accumulators by funnel shifts -- 1.5 instructions per
 // decision bit instead of FSETP + predicated IMAD.  Planes 0-3 are accumulated inverted (bit = "differs
 // from the maximum") and complemented at the flush.  Every score is finite here (|x| <= FLT_MAX and the
@@ -126,19 +98,29 @@ __device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
     asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
 }
+// The producer's side of that hand-off: one 64-bit relaxed store at gpu scope (a plain weak store racing
+// with the relaxed polls would be a data race under the PTX memory model).  The inter-pair scheme reads
+// the row back from the same warp after __syncwarp(): a plain store.
+template <bool WAVE>
+__device__ __forceinline__ void st_boundary(float2* p, float x, float y) {
+    if(WAVE) asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+    else *p = make_float2(x, y);
+}
 constexpr uint32_t WAVE_BLOCK = 32;  // columns of the row above fetched per refill (one per lane)
 
 // NC = substitution-table columns kept per lane: 16 (all IUPAC codes) or 4 when no descendant of the
 // batch carries an ambiguity code (the common case) -- a quarter of the shared memory, so more
 // resident warps to fill issue slots.
-// SGN = decisions by sign-shift (COATI_ROWPAIR_SGN) instead of FSETP + predicated IMAD.
-template <int R, bool WAVE, int NC, bool SGN = false>
+// nc_flag (raw-sequence batches): device word set by encode_pairs_kernel when any descendant carries an
+// ambiguity code; both NC variants are launched and the one that does not apply returns at once, so the
+// host never waits for the flag.
+template <int R, bool WAVE, int NC>
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
                      float4* __restrict__ bnd_all, uint32_t bnd_stride, uint8_t* __restrict__ dirs,
-                     PairResult* __restrict__ results, uint32_t* __restrict__ prog) {
+                     PairResult* __restrict__ results, const unsigned int* __restrict__ nc_flag) {
     static_assert(R % 2 == 0, "rows are processed in pairs");
     constexpr int R4 = (R + 3) / 4;
     constexpr int H = 32 * R;
@@ -147,12 +129,11 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* s_tab = s_dyn + (size_t)warp * R4 * NC * 32;
     float2* bnd = reinterpret_cast<float2*>(bnd_all + ((size_t)blockIdx.x * PIPE_WARPS + warp) * 2 * bnd_stride);
-    (void)prog;
+    if(nc_flag && ((*nc_flag != 0) != (NC == 16))) return;
     const uint32_t FULL = 0xffffffffu;
     const int rot = (lane + 31) & 31;
     const f2 ng2 = mk2(g.ng, g.ng), go2 = mk2(g.go, g.go), gs2 = mk2(g.gs, g.gs), ge2 = mk2(g.ge, g.ge);
     const char* tab_lane = reinterpret_cast<const char*>(s_tab) + lane * 16;
-    const uint32_t one = g.k;  // == 1, but opaque to the compiler: keeps the accumulate an IMAD
 
     for(;;) {
         uint32_t p = first, band0 = 0;
@@ -280,38 +261,23 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     bl = *pb++;
                 }
                 if(u < lb) {
-                    const uint32_t bm = 1u << (31 - (t & 31));
                     float sv[R4 * 4];
 #pragma unroll
                     for(int h = 0; h < R4; ++h) {
                         const float4 v = *reinterpret_cast<const float4*>(tab_lane + bo + h * (NC * 512));
                         sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
                     }
-                    float D = recvY, dXq = diagX;
-                    float Mv[R];  // SGN: every match score first, from the previous column's X
-                    if(SGN) {
-                        Mv[0] = diagX + sv[0];
+                    float D = recvY;
+                    float Mv[R];  // every match score first, from the previous column's X
+                    Mv[0] = diagX + sv[0];
 #pragma unroll
-                        for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
-                    }
+                    for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
 #pragma unroll
-                    for(int q = 0; q < R; q += 2) {
-                        if(SGN) {
-                            COATI_ROWPAIR_SGN(q)
-                            continue;
-                        }
-                        const f2 M2 = add2(mk2(dXq, Xp[q]), mk2(sv[q], sv[q + 1]));
-                        const f2 I2 = mk2(Zp[q], Zp[q + 1]);
-                        const f2 t1 = add2(M2, ng2), xm = add2(t1, ng2), ym = add2(t1, go2), zm = add2(M2, go2);
-                        const f2 t2 = add2(I2, gs2), xi = add2(t2, ng2), yi = add2(t2, go2), zi = add2(I2, ge2);
-                        dXq = Xp[q + 1];
-                        COATI_ROW(q, lo2(xm), lo2(ym), lo2(zm), lo2(xi), lo2(yi), lo2(zi))
-                        COATI_ROW(q + 1, hi2(xm), hi2(ym), hi2(zm), hi2(xi), hi2(yi), hi2(zi))
-                    }
+                    for(int q = 0; q < R; q += 2) COATI_ROWPAIR_SGN(q)
                     outX = Xp[R - 1];
                     outY = D;
                     diagX = recvX;
-                    if(lane == 31) bout[u + 1] = make_float2(outX, outY);
+                    if(lane == 31) st_boundary<WAVE>(bout + u + 1, outX, outY);
                 }
                 boff = bo;
                 if(lane == 31) {
@@ -326,14 +292,12 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     uint32_t w[WPL];
 #pragma unroll
                     for(int x = 0; x < (int)WPL; ++x) w[x] = x < 5 * R ? acc[x / 5][x % 5] : 0u;
-                    if(SGN) {
-                        // bits were pushed in at the bottom: the lane's last column of this block goes
-                        // to bit 31 - step % 32 (a lane that ends inside the block stopped pushing early)
-                        const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
-                        const uint32_t sh = 31u - (t_end & 31u);
+                    // bits were pushed in at the bottom: the lane's last column of this block goes
+                    // to bit 31 - step % 32 (a lane that ends inside the block stopped pushing early)
+                    const uint32_t t_end = min(t, lb - 1 + (uint32_t)lane);
+                    const uint32_t sh = 31u - (t_end & 31u);
 #pragma unroll
-                        for(int x = 0; x < 5 * R; ++x) w[x] = (x % 5 < 4 ? ~w[x] : w[x]) << sh;
-                    }
+                    for(int x = 0; x < 5 * R; ++x) w[x] = (x % 5 < 4 ? ~w[x] : w[x]) << sh;
 #pragma unroll
                     for(int x = 0; x < (int)WPL / 4; ++x)
                         dst[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
@@ -360,7 +324,6 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     }
 }
 
-#undef COATI_ROW
 #undef COATI_ROWPAIR_SGN
 
 }  // namespace coati_gpu

@@ -1,7 +1,7 @@
 // K = 3 (codon-unit gaps, `-k 3`) specialisation of the register-pipelined inter-pair Viterbi fill:
 // the scheme, the decision-plane stream (PipeLayout) and the exactness argument of viterbi_pipe.cuh,
 // with the issue-slot tuning of viterbi_pipe1.cuh (packed add.rn.f32x2 for the match/insert halves of
-// row pairs, FSETP + predicated IMAD for the decisions, lane 31 carrying lane 0's inputs).
+// row pairs, sign-shift decisions, lane 31 carrying lane 0's inputs).
 //
 // What K = 3 changes (src/lib/align_pair.cc:97-124 with look_back = 3):
 //   D(r, c) comes from row r-3: the three bottom rows of a lane go to the lane below (3 shuffles),
@@ -56,7 +56,7 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
                      float4* __restrict__ bnd_all, uint32_t bnd_stride, uint8_t* __restrict__ dirs,
-                     PairResult* __restrict__ results, uint32_t* __restrict__) {
+                     PairResult* __restrict__ results, const unsigned int* __restrict__ nc_flag) {
     static_assert(R % 6 == 0, "rows are processed in pairs and handed over in threes");
     constexpr int K = 3;
     constexpr int R4 = (R + 3) / 4;
@@ -71,6 +71,7 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     const f2 ng2 = mk2(g.ng, g.ng), go2 = mk2(g.go, g.go), gs2 = mk2(g.gs, g.gs), ge2 = mk2(g.ge, g.ge);
     const f2 gk12 = mk2(g.gk1, g.gk1), gk2 = mk2(g.gk, g.gk);
     const char* tab_lane = reinterpret_cast<const char*>(s_tab) + lane * 16;
+    if(nc_flag && ((*nc_flag != 0) != (NC == 16))) return;  // see viterbi_pipe1.cuh
 
     for(;;) {
         uint32_t p = 0;
@@ -220,7 +221,6 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
     }
 }
 
-#undef COATI_ROW3
 #undef COATI_ROWPAIR3_SGN
 
 }  // namespace coati_gpu

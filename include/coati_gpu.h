@@ -152,7 +152,9 @@ void coati_synth_fill(uint64_t seed, uint64_t first, uint64_t n, int workload, d
  *                       Seed(state_type)), in-out, so a host `Random` stays in lock-step.
  *                       out_a/out_b: n rows of stride La+Lb+1 bytes, NUL-terminated; scores[n].
  * coati_gpu_forward_terminal: the adjusted terminal M, D, I (align_pair.cc:130-138); the forward
- *                       log-likelihood is log_sum_exp of the three. */
+ *                       log-likelihood is log_sum_exp of the three.
+ * A handle belongs to the model it was filled under: after coati_gpu_set_model(s) on its context,
+ * coati_gpu_sampleback on an older handle returns COATI_GPU_E_ARG (fill again). */
 int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b, size_t Lb,
                       coati_gpu_forward_t** handle);
 int coati_gpu_forward_terminal(coati_gpu_forward_t* handle, float term[3], float* fill_ms);

@@ -229,3 +229,32 @@ def alignment_score(aln_a: str, aln_b: str, table, g=DEFAULT_G, e=DEFAULT_E, k=1
     if rc != 0:
         raise ValueError(f"alignment_score rc={rc}")
     return np.float32(sc.value)
+
+
+def path_score(aln_a: str, aln_b: str, a, b, table, g=DEFAULT_G, e=DEFAULT_E, k=1):
+    """The alignment rows re-scored through forward_impl's own transition terms and association
+    (align_pair.cc:81-138, oracle/long_pair.c).  For k = 1 this must equal the Viterbi score bit for bit."""
+    a, b, t = _u8(a), _u8(b), _table(table)
+    if len(aln_a) != len(aln_b):
+        raise ValueError("rows differ in length")
+    sc = C.c_float(0)
+    rc = lib.orc_path_score(aln_a.encode(), aln_b.encode(), C.c_size_t(len(aln_a)), _ptr(a, _c_u8p),
+                            C.c_size_t(len(a)), _ptr(b, _c_u8p), C.c_size_t(len(b)), _ptr(t, _c_fp),
+                            C.c_float(g), C.c_float(e), C.c_size_t(k), C.byref(sc))
+    if rc != 0:
+        raise ValueError(f"path_score: rows are not an alignment of the pair (rc={rc})")
+    return np.float32(sc.value)
+
+
+def viterbi_score(a, b, table, g=DEFAULT_G, e=DEFAULT_E, k=1, threads=None):
+    """Score-only rolling-row Viterbi, O(Lb) memory per strip, one strip of rows per thread
+    (oracle/long_pair.c): max of the adjusted terminal M, D, I (align_pair.cc:130-138, :265)."""
+    a, b, t = _u8(a), _u8(b), _table(table)
+    sc = C.c_float(0)
+    threads = int(threads or os.cpu_count() or 1)
+    rc = lib.orc_viterbi_score(_ptr(a, _c_u8p), C.c_size_t(len(a)), _ptr(b, _c_u8p), C.c_size_t(len(b)),
+                               _ptr(t, _c_fp), C.c_float(g), C.c_float(e), C.c_size_t(k), C.c_int(threads),
+                               C.byref(sc))
+    if rc != 0:
+        raise RuntimeError(f"viterbi_score failed rc={rc}")
+    return np.float32(sc.value)

@@ -71,6 +71,15 @@ float orc_end_stop_gap_score(float g, float e);
 int orc_alignment_score(const char* aln_a, const char* aln_b, size_t n, const float* table,
                         float g, float e, size_t k, float* score);
 
+/* long_pair.c: exact O(La + Lb)-memory validators for pairs the full matrices cannot hold.
+ * orc_path_score: the alignment rows re-scored through forward_impl's own transition terms
+ * (align_pair.cc:81-138); orc_viterbi_score: score-only rolling-row Viterbi, k = 1, `threads` strips. */
+int orc_path_score(const char* aln_a, const char* aln_b, size_t n, const uint8_t* a, size_t la,
+                   const uint8_t* b, size_t lb, const float* table, float g, float e, size_t k,
+                   float* score);
+int orc_viterbi_score(const uint8_t* a, size_t la, const uint8_t* b, size_t lb, const float* table,
+                      float g, float e, size_t k, int threads, float* score);
+
 #ifdef __cplusplus
 }
 #endif

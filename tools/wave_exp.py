@@ -8,7 +8,7 @@ for name in ("example-10k", "example-40k", "example-160k"):
     (_, anc), (_, des) = util.load_fasta(name)
     anc = util.sanitise_ancestor(anc)
     a, b = oracle.encode_pair(anc, des)
-    for R in (2, 4, 8):
+    for R in (2, 4, 8, 10):
         os.environ["COATI_GPU_WAVE_R"] = str(R)
         ctx = coati_b200.Context(0)
         ctx.set_model(T)
