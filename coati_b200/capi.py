@@ -90,6 +90,9 @@ def load_library() -> C.CDLL:
     lib.coati_gpu_forward_terminal.argtypes = [vp, _fp, _fp]
     lib.coati_gpu_sampleback.argtypes = [vp, C.c_char_p, C.c_char_p, _u64p, C.c_size_t, vp, vp,
                                          C.POINTER(C.c_size_t), _fp, _fp]
+    lib.coati_gpu_forward_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, C.POINTER(vp)]
+    lib.coati_gpu_forward_batch_terminal.argtypes = [vp, _fp, _fp, _fp]
+    lib.coati_gpu_sampleback_batch.argtypes = [vp, vp, vp, _u64p, C.c_size_t, vp, vp, _u64p, _fp, _fp]
     lib.coati_gpu_forward_free.argtypes = [vp]
     lib.coati_gpu_forward_free.restype = None
     lib.coati_gpu_forward_matrices.argtypes = [vp, _fp, _fp, _fp]
@@ -240,6 +243,60 @@ class Forward:
             pass
 
 
+class ForwardBatch:
+    """Forward matrices of a batch of pairs (coati_gpu_forward_batch) + per-pair seeded sampling."""
+
+    def __init__(self, ctx: "Context", pack: "PackedPairs"):
+        self.ctx, self.lib, self.pack = ctx, ctx.lib, pack
+        self.h = C.c_void_p()
+        ctx._check(self.lib.coati_gpu_forward_batch(ctx.h, pack.n, _vp(pack.a_all), pack.a_off.ctypes.data_as(_u64p),
+                                                    _vp(pack.b_all), pack.b_off.ctypes.data_as(_u64p), C.byref(self.h)))
+
+    def terminal(self):
+        """(term[npairs, 3], loglik[npairs], fill_ms)"""
+        n = self.pack.n
+        term = np.zeros((n, 3), dtype=np.float32)
+        ll = np.zeros(n, dtype=np.float32)
+        ms = C.c_float(0)
+        self.ctx._check(self.lib.coati_gpu_forward_batch_terminal(self.h, term.ctypes.data_as(_fp),
+                                                                  ll.ctypes.data_as(_fp), C.byref(ms)))
+        return term, ll, ms.value
+
+    def sampleback(self, states, n: int):
+        """states: uint64[npairs, 2].  Returns (rows[p][s] = (row_a, row_b), scores[npairs, n], new states, ms)."""
+        pk = self.pack
+        npairs = pk.n
+        total = n * (int(pk.a_off[-1]) + int(pk.b_off[-1]) + npairs)
+        oa = np.zeros(total + 1, dtype=np.uint8)
+        ob = np.zeros(total + 1, dtype=np.uint8)
+        ol = np.zeros(max(1, npairs * n), dtype=np.uint64)
+        sc = np.zeros(max(1, npairs * n), dtype=np.float32)
+        st = np.ascontiguousarray(states, dtype=np.uint64).reshape(npairs, 2).copy()
+        ms = C.c_float(0)
+        self.ctx._check(self.lib.coati_gpu_sampleback_batch(self.h, _vp(pk.anc_all), _vp(pk.des_all),
+                                                            st.ctypes.data_as(_u64p), n, _vp(oa), _vp(ob),
+                                                            ol.ctypes.data_as(_u64p), sc.ctypes.data_as(_fp), C.byref(ms)))
+        rows = []
+        for p in range(npairs):
+            base = n * (int(pk.a_off[p]) + int(pk.b_off[p]) + p)
+            stride = int(pk.a_off[p + 1] - pk.a_off[p]) + int(pk.b_off[p + 1] - pk.b_off[p]) + 1
+            rows.append([(oa[base + s * stride: base + s * stride + int(ol[p * n + s])].tobytes().decode("latin-1"),
+                          ob[base + s * stride: base + s * stride + int(ol[p * n + s])].tobytes().decode("latin-1"))
+                         for s in range(n)])
+        return rows, sc[:npairs * n].reshape(npairs, n), st, ms.value
+
+    def free(self):
+        if self.h:
+            self.lib.coati_gpu_forward_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU context (coati_gpu_ctx).  Raises CoatiGpuError on any failure -- never falls back."""
 
@@ -344,6 +401,9 @@ class Context:
             rows_a.append(out_a[o:o + n].tobytes().decode("latin-1"))
             rows_b.append(out_b[o:o + n].tobytes().decode("latin-1"))
         return rows_a, rows_b, score, status
+
+    def forward_batch(self, pack: "PackedPairs") -> "ForwardBatch":
+        return ForwardBatch(self, pack)
 
     def forward(self, a, b) -> "Forward":
         return Forward(self, a, b)

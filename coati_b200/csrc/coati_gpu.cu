@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "forward.cuh"
+#include "forward_band.cuh"
 #include "sample_spec.cuh"
 #include "traceback.cuh"
 #include "viterbi_generic.cuh"
@@ -160,6 +161,8 @@ struct coati_gpu_ctx {
     bool tb_serial = false;  // COATI_GPU_TB_SERIAL=1: long pairs walked one column at a time (A/B)
     uint32_t force_r = 0;  // COATI_GPU_FORCE_R: rows per lane of every inter-pair fill (tuning)
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
+    bool forward_generic = false;  // COATI_GPU_FORWARD_GENERIC=1: the any-k Forward kernel also for k = 1 (A/B)
+    int fwd_ctas_per_sm[2] = {1, 1};  // forward_band_kernel<false>, <true>
     bool sample_serial = false;  // COATI_GPU_SAMPLE_SERIAL=1: one thread draws all samples (A/B)
     bool pipe_scalar = false;  // COATI_GPU_PIPE_SCALAR=1: scalar template instead of the FADD2 kernels (A/B)
     int ctas_per_sm[32] = {};  // per entry of the kernel registry, on this device
@@ -403,6 +406,16 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     if(const char* env = std::getenv("COATI_GPU_FORCE_GENERIC")) ctx->force_generic = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_PIPE_SCALAR")) ctx->pipe_scalar = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_SAMPLE_SERIAL")) ctx->sample_serial = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_FORWARD_GENERIC")) ctx->forward_generic = env[0] == '1';
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd_ctas_per_sm[0], forward_band_kernel<false>,
+                                                     FB_WARPS * 32, 0) != cudaSuccess ||
+       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd_ctas_per_sm[1], forward_band_kernel<true>,
+                                                     FB_WARPS * 32, 0) != cudaSuccess ||
+       ctx->fwd_ctas_per_sm[0] < 1 || ctx->fwd_ctas_per_sm[1] < 1) {
+        cudaGetLastError();
+        coati_gpu_shutdown(ctx);
+        return COATI_GPU_E_CUDA;
+    }
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_TB_SERIAL")) ctx->tb_serial = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_FORCE_R")) ctx->force_r = (uint32_t)std::atoi(env);
@@ -1373,10 +1386,14 @@ extern "C" int coati_gpu_viterbi_directions(coati_gpu_ctx* ctx, const uint8_t* a
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward fill + sampleback (one pair per handle)
+// Forward fill + sampleback: a handle owns the state matrices of one pair or of a batch of pairs
 struct coati_gpu_forward_t {
     coati_gpu_ctx* ctx = nullptr;
-    uint32_t la = 0, lb = 0;
+    size_t npairs = 1;
+    uint32_t la = 0, lb = 0;       // of pair 0 (the single-pair entry points)
+    std::vector<FwdDesc> descs;    // a_off / b_off relative to the first pair's; mat_off in floats
+    std::vector<uint64_t> out_off; // batch sampling: first row byte of every pair (for n samples)
+    uint64_t a_total = 0, b_total = 0;
     DevBuf<uint8_t> d_a, d_b;
     DevBuf<char> d_anc, d_des, d_out_a, d_out_b;
     DevBuf<FwdDesc> d_desc;
@@ -1384,12 +1401,14 @@ struct coati_gpu_forward_t {
     DevBuf<uint64_t> d_rng, d_out_off;
     DevBuf<uint32_t> d_len, d_start;
     DevBuf<int32_t> d_status;
+    DevBuf<unsigned int> d_counter;
     DevBuf<SampleRec> d_rec;   // per (cell, state) sampling records (sample_spec.cuh), built lazily
     DevBuf<U128> d_pw;         // MULT^(2^i)
     DevBuf<uint32_t> d_draws;
     DevBuf<uint64_t> d_starts, d_cursor;
     bool rec_ready = false;
     uint64_t model_gen = 0;  // the context's model when the matrices were filled
+    std::vector<float> terms;  // adjusted terminal M, D, I per pair
     float term[3] = {0, 0, 0};
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float fill_ms = 0, sample_ms = 0;
@@ -1399,33 +1418,53 @@ struct coati_gpu_forward_t {
     }
 };
 
-extern "C" int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
-                                 size_t Lb, coati_gpu_forward_t** out) {
-    if(!ctx || !out || !ctx->model_set || (La && !a) || (Lb && !b)) return COATI_GPU_E_ARG;
+// forward (align_pair.cc:149-152) for npairs pairs (CSR); offsets may start anywhere
+static int forward_fill(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all, const uint64_t* a_off,
+                        const uint8_t* b_all, const uint64_t* b_off, coati_gpu_forward_t** out) {
+    if(!ctx || !out || !ctx->model_set || npairs == 0 || !a_off || !b_off || npairs > 0x7fffffffull)
+        return COATI_GPU_E_ARG;
     *out = nullptr;
-    if(La > 0x7fffffffull || Lb > 0x7fffffffull) return COATI_GPU_E_ARG;
-    if(La % ctx->gap.k != 0 || Lb % ctx->gap.k != 0) return COATI_GPU_E_LENGTH;
-    for(size_t x = 0; x < La; ++x)
-        if(a[x] >= TABLE_ROWS) return COATI_GPU_E_SYMBOL;
-    for(size_t x = 0; x < Lb; ++x)
-        if(b[x] >= TABLE_COLS) return COATI_GPU_E_SYMBOL;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t k = ctx->gap.k;
     std::unique_ptr<coati_gpu_forward_t> h(new(std::nothrow) coati_gpu_forward_t);
     if(!h) return COATI_GPU_E_NOMEM;
     h->ctx = ctx;
     h->model_gen = ctx->model_gen;
-    h->la = (uint32_t)La;
-    h->lb = (uint32_t)Lb;
-    const uint64_t plane = (uint64_t)(La + 1) * (Lb + 1);
+    h->npairs = npairs;
+    const uint64_t a0 = a_off[0], b0 = b_off[0];
+    h->a_total = a_off[npairs] - a0;
+    h->b_total = b_off[npairs] - b0;
+    if((h->a_total && !a_all) || (h->b_total && !b_all)) return COATI_GPU_E_ARG;
+    uint64_t mat_total = 0;
+    try {
+        h->descs.resize(npairs);
+        h->terms.assign(3 * npairs, 0.0f);
+    } catch(const std::bad_alloc&) {
+        return COATI_GPU_E_NOMEM;
+    }
+    for(size_t p = 0; p < npairs; ++p) {
+        const uint64_t La = a_off[p + 1] - a_off[p], Lb = b_off[p + 1] - b_off[p];
+        if(La > 0x7fffffffull || Lb > 0x7fffffffull) return COATI_GPU_E_ARG;
+        if(La % k != 0 || Lb % k != 0) return COATI_GPU_E_LENGTH;
+        for(uint64_t x = a_off[p]; x < a_off[p + 1]; ++x)
+            if(a_all[x] >= TABLE_ROWS) return COATI_GPU_E_SYMBOL;
+        for(uint64_t x = b_off[p]; x < b_off[p + 1]; ++x)
+            if(b_all[x] >= TABLE_COLS) return COATI_GPU_E_SYMBOL;
+        h->descs[p] = FwdDesc{a_off[p] - a0, b_off[p] - b0, mat_total, (uint32_t)La, (uint32_t)Lb};
+        mat_total += 3 * (La + 1) * (Lb + 1);
+    }
+    h->la = h->descs[0].la;
+    h->lb = h->descs[0].lb;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) {
         if(e == cudaSuccess) e = r;
     };
-    ok(h->d_a.alloc(La + 1, &ctx->pool));
-    ok(h->d_b.alloc(Lb + 1, &ctx->pool));
-    ok(h->d_desc.alloc(1, &ctx->pool));
-    ok(h->d_mats.alloc(3 * plane, &ctx->pool));
-    ok(h->d_term.alloc(4, &ctx->pool));
+    ok(h->d_a.alloc(h->a_total + 1, &ctx->pool));
+    ok(h->d_b.alloc(h->b_total + 1, &ctx->pool));
+    ok(h->d_desc.alloc(npairs, &ctx->pool));
+    ok(h->d_mats.alloc(mat_total, &ctx->pool));
+    ok(h->d_term.alloc(3 * npairs + 1, &ctx->pool));
+    ok(h->d_counter.alloc(npairs + 1, &ctx->pool));
     if(e != cudaSuccess) {
         ctx->last_error = std::string("forward allocation: ") + cudaGetErrorString(e);
         cudaGetLastError();
@@ -1433,20 +1472,162 @@ extern "C" int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La
     }
     for(cudaEvent_t& ev : h->ev) CU_TRY(ctx, cudaEventCreate(&ev));
     cudaStream_t s = ctx->stream;
-    FwdDesc fd{0, 0, 0, (uint32_t)La, (uint32_t)Lb};
-    CU_TRY(ctx, cudaMemcpyAsync(h->d_desc.p, &fd, sizeof(fd), cudaMemcpyHostToDevice, s));
-    if(La) CU_TRY(ctx, cudaMemcpyAsync(h->d_a.p, a, La, cudaMemcpyHostToDevice, s));
-    if(Lb) CU_TRY(ctx, cudaMemcpyAsync(h->d_b.p, b, Lb, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->d_desc.p, h->descs.data(), npairs * sizeof(FwdDesc), cudaMemcpyHostToDevice, s));
+    if(h->a_total) CU_TRY(ctx, cudaMemcpyAsync(h->d_a.p, a_all + a0, h->a_total, cudaMemcpyHostToDevice, s));
+    if(h->b_total) CU_TRY(ctx, cudaMemcpyAsync(h->d_b.p, b_all + b0, h->b_total, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemsetAsync(h->d_counter.p, 0, (npairs + 1) * sizeof(unsigned int), s));
     CU_TRY(ctx, cudaEventRecord(h->ev[0], s));
-    forward_fill_kernel<<<1, 1023, 0, s>>>(h->d_desc.p, 1, h->d_a.p, h->d_b.p, ctx->d_table, ctx->gap,
-                                          h->d_mats.p, h->d_term.p);
-    ++ctx->launches;
+    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+    if(k != 1 || ctx->forward_generic) {
+        // any gap unit length: CTA per pair, anti-diagonal sweep over the stored planes (forward.cuh)
+        forward_fill_kernel<<<(unsigned)std::min<size_t>(npairs, 4 * sms), 1023, 0, s>>>(
+            h->d_desc.p, (uint32_t)npairs, h->d_a.p, h->d_b.p, ctx->d_table, ctx->gap, h->d_mats.p, h->d_term.p);
+        ++ctx->launches;
+    } else if(npairs <= 16) {
+        // few pairs: each as a wavefront of 10-row bands over the whole GPU; stored values are their own
+        // ready flags, so the matrices start as NaN
+        CU_TRY(ctx, cudaMemsetAsync(h->d_mats.p, 0xff, mat_total * sizeof(float), s));
+        for(size_t p = 0; p < npairs; ++p) {
+            const uint32_t nbands = std::max(1u, (h->descs[p].la + FB_ROWS - 1) / FB_ROWS);
+            const uint32_t grid = std::min((nbands + FB_WARPS - 1) / FB_WARPS, sms * (uint32_t)ctx->fwd_ctas_per_sm[1]);
+            forward_band_kernel<true><<<grid, FB_WARPS * 32, 0, s>>>(
+                h->d_desc.p, (uint32_t)p, (uint32_t)p + 1, h->d_counter.p + p, h->d_a.p, h->d_b.p, ctx->d_table,
+                ctx->gap, h->d_mats.p, h->d_term.p);
+            ++ctx->launches;
+        }
+    } else {
+        const uint32_t grid = (uint32_t)std::min<size_t>((npairs + FB_WARPS - 1) / FB_WARPS,
+                                                         (size_t)sms * ctx->fwd_ctas_per_sm[0]);
+        forward_band_kernel<false><<<grid, FB_WARPS * 32, 0, s>>>(
+            h->d_desc.p, 0, (uint32_t)npairs, h->d_counter.p, h->d_a.p, h->d_b.p, ctx->d_table, ctx->gap,
+            h->d_mats.p, h->d_term.p);
+        ++ctx->launches;
+    }
     CU_TRY(ctx, cudaEventRecord(h->ev[1], s));
-    CU_TRY(ctx, cudaMemcpyAsync(h->term, h->d_term.p, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->terms.data(), h->d_term.p, 3 * npairs * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU_TRY(ctx, cudaStreamSynchronize(s));
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaEventElapsedTime(&h->fill_ms, h->ev[0], h->ev[1]));
+    for(int x = 0; x < 3; ++x) h->term[x] = h->terms[x];
     *out = h.release();
+    return COATI_GPU_OK;
+}
+
+extern "C" int coati_gpu_forward(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,
+                                 size_t Lb, coati_gpu_forward_t** out) {
+    if((La && !a) || (Lb && !b)) return COATI_GPU_E_ARG;
+    const uint64_t a_off[2] = {0, La}, b_off[2] = {0, Lb};
+    return forward_fill(ctx, 1, a, a_off, b, b_off, out);
+}
+
+extern "C" int coati_gpu_forward_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
+                                       const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
+                                       coati_gpu_forward_t** out) {
+    return forward_fill(ctx, npairs, a_all, a_off, b_all, b_off, out);
+}
+
+extern "C" int coati_gpu_forward_batch_terminal(coati_gpu_forward_t* h, float* term, float* loglik,
+                                                float* fill_ms) {
+    if(!h) return COATI_GPU_E_ARG;
+    for(size_t p = 0; p < h->npairs; ++p) {
+        const float* t = &h->terms[3 * p];
+        if(term)
+            for(int x = 0; x < 3; ++x) term[3 * p + x] = t[x];
+        if(loglik) {
+            // log_sum_exp(log_sum_exp(M, D), I) with the host libm (utils.hpp:134-156)
+            auto l1pe = [](float x) -> float {
+                if(x <= -16.0f) return ::expf(x);
+                if(x <= 8.0f) return ::log1pf(::expf(x));
+                if(x <= 14.5f) return x + ::expf(-x);
+                return x;
+            };
+            auto lse = [&](float a, float b) -> float { return std::max(a, b) + l1pe(-std::fabs(a - b)); };
+            loglik[p] = lse(lse(t[0], t[1]), t[2]);
+        }
+    }
+    if(fill_ms) *fill_ms = h->fill_ms;
+    return COATI_GPU_OK;
+}
+
+// n serial samplebacks per pair, every pair on its own RNG stream (one thread per pair): the batch form of
+// marg_sample's loop (align_marginal.cc:589-593).  rng_states: 2 x uint64 per pair, in-out.  Rows of
+// sample s of pair p start at byte n * (a_off[p] + b_off[p] + p) + s * (La_p + Lb_p + 1) (offsets relative
+// to the first pair's); out_len / scores are [p * n + s].
+extern "C" int coati_gpu_sampleback_batch(coati_gpu_forward_t* h, const char* anc_all, const char* des_all,
+                                          uint64_t* rng_states, size_t n, char* out_a, char* out_b,
+                                          uint64_t* out_len, float* scores, float* sample_ms) {
+    if(!h || !rng_states || (n && (!out_a || !out_b)) || n > 0x7fffffffull) return COATI_GPU_E_ARG;
+    if((h->a_total && !anc_all) || (h->b_total && !des_all)) return COATI_GPU_E_ARG;
+    coati_gpu_ctx* ctx = h->ctx;
+    if(h->model_gen != ctx->model_gen) return COATI_GPU_E_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t np = h->npairs;
+    const uint64_t out_total = n * (h->a_total + h->b_total + np);
+    std::vector<uint64_t> st(2 * np);
+    try {
+        h->out_off.resize(np);
+    } catch(const std::bad_alloc&) {
+        return COATI_GPU_E_NOMEM;
+    }
+    for(size_t p = 0; p < np; ++p) {
+        h->out_off[p] = n * (h->descs[p].a_off + h->descs[p].b_off + p);
+        st[2 * p] = rng_states[2 * p] | 1ull;  // Lehmer64Fast::SetState (random.hpp:131-134)
+        st[2 * p + 1] = rng_states[2 * p + 1];
+    }
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) {
+        if(e == cudaSuccess) e = r;
+    };
+    ok(h->d_anc.alloc(h->a_total + 1, &ctx->pool));
+    ok(h->d_des.alloc(h->b_total + 1, &ctx->pool));
+    ok(h->d_out_a.alloc(out_total + 1, &ctx->pool));
+    ok(h->d_out_b.alloc(out_total + 1, &ctx->pool));
+    ok(h->d_rng.alloc(2 * np, &ctx->pool));
+    ok(h->d_out_off.alloc(np, &ctx->pool));
+    ok(h->d_len.alloc(np * n + 1, &ctx->pool));
+    ok(h->d_start.alloc(np * n + 1, &ctx->pool));
+    ok(h->d_scores.alloc(np * n + 1, &ctx->pool));
+    ok(h->d_status.alloc(np, &ctx->pool));
+    if(e != cudaSuccess) {
+        ctx->last_error = std::string("sampleback allocation: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return COATI_GPU_E_NOMEM;
+    }
+    if(h->a_total) CU_TRY(ctx, cudaMemcpyAsync(h->d_anc.p, anc_all, h->a_total, cudaMemcpyHostToDevice, s));
+    if(h->b_total) CU_TRY(ctx, cudaMemcpyAsync(h->d_des.p, des_all, h->b_total, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->d_rng.p, st.data(), st.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(h->d_out_off.p, h->out_off.data(), np * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaEventRecord(h->ev[1], s));
+    sampleback_kernel<<<(unsigned)((np + 31) / 32), 32, 0, s>>>(
+        h->d_desc.p, (uint32_t)np, h->d_mats.p, h->d_term.p, ctx->d_table, h->d_a.p, h->d_b.p, h->d_anc.p,
+        h->d_des.p, ctx->gap, h->d_rng.p, (uint32_t)n, h->d_out_off.p, h->d_out_a.p, h->d_out_b.p, h->d_len.p,
+        h->d_start.p, h->d_scores.p, h->d_status.p);
+    if(n)
+        compact_samples_kernel<<<(unsigned)((np * n + 7) / 8), 256, 0, s>>>(
+            h->d_desc.p, (uint32_t)np, (uint32_t)n, h->d_out_off.p, h->d_out_a.p, h->d_out_b.p, h->d_len.p,
+            h->d_start.p);
+    ctx->launches += 2;
+    CU_TRY(ctx, cudaEventRecord(h->ev[2], s));
+    std::vector<uint32_t> lens(np * n);
+    std::vector<int32_t> status(np);
+    if(n) {
+        CU_TRY(ctx, cudaMemcpyAsync(out_a, h->d_out_a.p, out_total, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(out_b, h->d_out_b.p, out_total, cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(lens.data(), h->d_len.p, np * n * 4, cudaMemcpyDeviceToHost, s));
+        if(scores) CU_TRY(ctx, cudaMemcpyAsync(scores, h->d_scores.p, np * n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(st.data(), h->d_rng.p, st.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(status.data(), h->d_status.p, np * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventElapsedTime(&h->sample_ms, h->ev[1], h->ev[2]));
+    if(sample_ms) *sample_ms = h->sample_ms;
+    if(out_len)
+        for(size_t x = 0; x < np * n; ++x) out_len[x] = lens[x];
+    for(size_t x = 0; x < 2 * np; ++x) rng_states[x] = st[x];
+    for(size_t p = 0; p < np; ++p)
+        if(status[p] != 0) return status[p];
     return COATI_GPU_OK;
 }
 
@@ -1459,7 +1640,7 @@ extern "C" int coati_gpu_forward_terminal(coati_gpu_forward_t* h, float term[3],
 }
 
 extern "C" int coati_gpu_forward_matrices(coati_gpu_forward_t* h, float* mch, float* del, float* ins) {
-    if(!h || !mch || !del || !ins) return COATI_GPU_E_ARG;
+    if(!h || !mch || !del || !ins || h->npairs != 1) return COATI_GPU_E_ARG;
     coati_gpu_ctx* ctx = h->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const uint64_t plane = (uint64_t)(h->la + 1) * (h->lb + 1);
@@ -1474,7 +1655,7 @@ extern "C" int coati_gpu_forward_matrices(coati_gpu_forward_t* h, float* mch, fl
 extern "C" int coati_gpu_sampleback(coati_gpu_forward_t* h, const char* anc, const char* des,
                                     uint64_t rng_state[2], size_t n, char* out_a, char* out_b,
                                     size_t* out_len, float* scores, float* sample_ms) {
-    if(!h || !rng_state || (n && (!out_a || !out_b))) return COATI_GPU_E_ARG;
+    if(!h || !rng_state || (n && (!out_a || !out_b)) || h->npairs != 1) return COATI_GPU_E_ARG;
     if((h->la && !anc) || (h->lb && !des) || n > 0x7fffffffull) return COATI_GPU_E_ARG;
     coati_gpu_ctx* ctx = h->ctx;
     // the matrices belong to the model they were filled under: sampling them with another table or other
@@ -1624,7 +1805,7 @@ extern "C" void coati_gpu_forward_free(coati_gpu_forward_t* h) {
 }
 
 extern "C" int coati_gpu_libm_eval(coati_gpu_ctx* ctx, int op, const float* in, float* out, size_t n) {
-    if(!ctx || !in || !out || op < 0 || op > 3) return COATI_GPU_E_ARG;
+    if(!ctx || !in || !out || op < 0 || op > 4) return COATI_GPU_E_ARG;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     DevBuf<float> d_in, d_out;
     if(d_in.alloc(n + 1, &ctx->pool) != cudaSuccess || d_out.alloc(n + 1, &ctx->pool) != cudaSuccess)

@@ -290,7 +290,8 @@ __global__ void libm_eval_kernel(int op, const float* __restrict__ in, float* __
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
     const float x = in[i];
-    out[i] = op == 0 ? libm_expf(x) : op == 1 ? libm_logf(x) : op == 2 ? libm_log1pf(x) : log1p_exp(x);
+    out[i] = op == 0 ? libm_expf(x) : op == 1 ? libm_logf(x) : op == 2 ? libm_log1pf(x) : op == 3 ? log1p_exp(x)
+                                                                                         : log1p_exp_neg(x);
 }
 
 }  // namespace coati_gpu

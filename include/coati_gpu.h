@@ -162,9 +162,24 @@ int coati_gpu_sampleback(coati_gpu_forward_t* handle, const char* anc, const cha
                          uint64_t rng_state[2], size_t n, char* out_a, char* out_b, size_t* out_len,
                          float* scores, float* sample_ms);
 void coati_gpu_forward_free(coati_gpu_forward_t* handle);
+
+/* Batch forms (the throughput path of `sample` / of a per-leaf sampling driver): forward for npairs pairs
+ * (CSR, as coati_gpu_viterbi_batch), one handle for all matrices; the adjusted terminal M, D, I (3 per pair)
+ * and the forward log-likelihood log_sum_exp(log_sum_exp(M, D), I) per pair; and n consecutive samplebacks
+ * per pair, every pair on its own RNG stream (rng_states: 2 x uint64 per pair, in-out).  Rows of sample s
+ * of pair p start at byte n * (a_off[p] + b_off[p] + p) + s * (La_p + Lb_p + 1), offsets relative to the
+ * first pair's, NUL-terminated; out_len / scores are [p * n + s]. */
+int coati_gpu_forward_batch(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all, const uint64_t* a_off,
+                            const uint8_t* b_all, const uint64_t* b_off, coati_gpu_forward_t** handle);
+int coati_gpu_forward_batch_terminal(coati_gpu_forward_t* handle, float* term, float* loglik,
+                                     float* fill_ms);
+int coati_gpu_sampleback_batch(coati_gpu_forward_t* handle, const char* anc_all, const char* des_all,
+                               uint64_t* rng_states, size_t n, char* out_a, char* out_b,
+                               uint64_t* out_len, float* scores, float* sample_ms);
 /* parity aids: the three state matrices in lattice coordinates, (La+1) x (Lb+1) row-major (the
  * reference's (La+k) x (Lb+k) matrices without their k-1 padding rows/columns); and the device
- * twins of libm (op 0: expf, 1: logf, 2: log1pf, 3: log1p_exp of utils.hpp:134-146) on an array. */
+ * twins of libm (op 0: expf, 1: logf, 2: log1pf, 3: log1p_exp of utils.hpp:134-146, 4: the branch-free
+ * log1p_exp the banded Forward kernel uses, defined for x <= 0) on an array. */
 int coati_gpu_forward_matrices(coati_gpu_forward_t* handle, float* mch, float* del, float* ins);
 int coati_gpu_libm_eval(coati_gpu_ctx* ctx, int op, const float* in, float* out, size_t n);
 

@@ -34,6 +34,11 @@ float orc_log1p_exp(float x) {
     return x;
 }
 
+/* the same over an array (tests compare device code with the host libm on whole ranges of floats) */
+void orc_log1p_exp_array(const float* in, float* out, size_t n) {
+    for(size_t x = 0; x < n; ++x) out[x] = orc_log1p_exp(in[x]);
+}
+
 /* ---- utils.hpp:152-156: log_sum_exp ------------------------------------------------- */
 float orc_log_sum_exp(float a, float b) {
     float x = fmax2(a, b);

@@ -26,6 +26,7 @@ enum {
 
 float orc_log1p_exp(float x);
 float orc_log_sum_exp(float a, float b);
+void orc_log1p_exp_array(const float* in, float* out, size_t n);
 
 int orc_fill(int semiring, const uint8_t* a, size_t la, const uint8_t* b, size_t lb,
              const float* table, float g, float e, size_t k, float* mch, float* del, float* ins,
