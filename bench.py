@@ -2,19 +2,24 @@
 """bench.py -- GCUPS / pairs-per-second of the marginal Gotoh Viterbi hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--pairs P] [--workload c5|c4]
+                    [--scaling strong|weak] [--no-cpu] [--no-extra]
 
-A "step" is one pass of the hot path (fill + traceback + row compaction) over one batch of
-synthetic codon-sequence pairs.  Default workload = BASELINE.json configs[4] (the configuration the
-metric is quoted on): 1 000 000 length-binned pairs {150,300,600,1200,2400} nt, mar-mg with
-omega=0.5 pi=0.25 t=0.05, k=1, seed 42 -- PER GPU (weak scaling: rank r takes pairs
-[r*P, (r+1)*P) of the same seeded stream; no data-path collective, results gathered to rank 0).
+A "step" is one pass of the hot path (fill + traceback + row expansion) over ONE batch of synthetic
+codon-sequence pairs.  Default workload = BASELINE.json configs[4] (the configuration the metric is quoted on):
+1 000 000 length-binned pairs {150,300,600,1200,2400} nt, mar-mg with omega=0.5 pi=0.25 t=0.05, k=1, seed 42.
 
-value  : whole-job GCUPS with inputs resident in HBM (CUDA events on the context's stream,
-         max over ranks)
-e2e    : same metric through the C ABI call a user makes (coati_gpu_alignpair_batch: raw sequences
-         in, aligned rows out) with pinned HOST buffers: validation + plan + H2D + encode + kernels +
-         D2H inside the timed region
-roofline / cpu_baseline: see DESIGN.md "Measurement".
+Multi-GPU (one process per GPU under torchrun), default `--scaling strong` = the config as written: the ONE
+batch lives in one shared, page-locked host arena; coati_gpu_plan_shards cuts it into contiguous chunks and
+gives them to the ranks by greedy longest-processing-time on the sum of La * Lb; no data-path collective.
+`--scaling weak` gives every rank its own P pairs (the round-1 definition).
+
+value  : whole-job GCUPS with inputs resident in HBM (CUDA events on the context's stream, max over ranks);
+         at N > 1 every step ends with the NCCL gather of all rows and result records to rank 0's device,
+         issued from a double-buffered staging copy on a side stream so it overlaps the next step's fill
+e2e    : same metric through the C ABI call a user makes (coati_gpu_alignpair_batch_ranges: raw sequences
+         in, aligned rows out) with pinned HOST arenas: validation + plan + H2D + encode + kernels + D2H inside
+         the timed region; at N > 1 every rank writes its pairs' rows into the one shared output arena
+roofline / cpu_baseline / extra: see DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -24,8 +29,8 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
+import uuid
 
 import numpy as np
 
@@ -36,11 +41,15 @@ FLOP_PER_CELL = 23          # 18 FADD + 5 FMAX of forward_impl's bo
 LANES_PER_SM = 128          # FP32 lanes per SM per clock
 WORKLOADS = {
     "c5": dict(id=5, k=1, table="mg_c5", pairs=1_000_000, seed=42,
+               model=dict(model="mar-mg", br_len=0.05, omega=0.5, pi=(0.25, 0.25, 0.25, 0.25)),
+               kernel="viterbi_pipe1_kernel<10,false,4>",
                desc="BASELINE configs[4]: length-binned pairs {150,300,600,1200,2400} nt "
                     "(40/30/20/8/2 %), mar-mg w=0.5 pi=0.25 t=0.05, k=1"),
     "c4": dict(id=4, k=3, table="ecm_default", pairs=100_000, seed=20240603,
+               model=dict(model="mar-ecm"), kernel="viterbi_pipe3_kernel<6,4>",
                desc="BASELINE configs[3]: 300-3000 nt pairs, mar-ecm, gap unit k=3"),
 }
+G_OPEN, G_EXT = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
 
 
 def parse_args():
@@ -50,9 +59,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the config's)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs of the batch (strong) / per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1-C4 / pageable records")
     return ap.parse_args()
 
 
@@ -120,87 +131,6 @@ def dist_env():
     return rank, world, local
 
 
-# ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(wl, npairs_total, seconds, threads, table, first=0):
-    """Time the reference's own viterbi_mem + traceback_viterbi (oracle/_ref, else the C port) on a
-    bounded, length-stratified sample of the same seeded workload.  Returns dict."""
-    import ctypes as C
-    import oracle
-    from coati_b200.capi import synth_pairs
-
-    kind = "reference" if oracle.ref is not None else "port"
-    # stratified sample: every (npairs_total // n)-th pair of the stream keeps the bin weights
-    est_gcups_core = 0.045
-    cells_per_pair = 338_000 if wl["id"] == 5 else 2_900_000
-    n = int(max(threads, min(npairs_total, seconds * est_gcups_core * 1e9 * threads / cells_per_pair)))
-    # pairs are i.i.d. draws of the seeded stream, so a contiguous block keeps the bin weights
-    w = synth_pairs(n, wl["id"], wl["seed"], first)
-    a_off, b_off = w["a_off"], w["b_off"]
-    la, lb = np.diff(a_off), np.diff(b_off)
-    a_all, anc_all, b_all, des_all = w["a_all"], w["anc_all"], w["b_all"], w["des_all"]
-    total = int(a_off[-1] + b_off[-1]) + n
-    out_a = np.zeros(total + 1, np.uint8)
-    out_b = np.zeros(total + 1, np.uint8)
-    out_len = np.zeros(n, np.uint64)
-    score = np.zeros(n, np.float32)
-    cells = float((la.astype(np.float64) * lb.astype(np.float64)).sum())
-    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
-    g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
-    if kind == "reference":
-        fn = oracle.ref.coati_ref_viterbi_batch
-        fn.restype = C.c_double
-        secs = fn(C.c_size_t(n), vp(a_all), vp(a_off), vp(b_all), vp(b_off), vp(anc_all), vp(des_all),
-                  vp(table), C.c_float(g), C.c_float(e), C.c_size_t(wl["k"]), C.c_int(threads),
-                  vp(out_a), vp(out_b), vp(out_len), vp(score))
-    else:
-        t0 = time.perf_counter()
-        for p in range(n):
-            sl_a = slice(int(a_off[p]), int(a_off[p + 1]))
-            sl_b = slice(int(b_off[p]), int(b_off[p + 1]))
-            oracle.viterbi(anc_all[sl_a].tobytes().decode(), des_all[sl_b].tobytes().decode(), table,
-                           g, e, wl["k"], enc=(a_all[sl_a], b_all[sl_b]))
-        secs = time.perf_counter() - t0
-        threads = 1
-    if secs <= 0:
-        raise RuntimeError("CPU reference run failed")
-    return dict(value=cells / secs / 1e9, unit="GCUPS", cores=threads, kind=kind, seconds=secs,
-                pairs=n, pairs_per_s=n / secs, cells=cells,
-                sample=f"first {n} pairs of the seeded {wl['desc'].split(':')[0]} stream (i.i.d. length bins, "
-                       f"{cells:.3g} cells), viterbi_mem+traceback_viterbi, {threads} threads")
-
-
-def run_reference(args, wl, table):
-    rank, world, local = dist_env()
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    npairs = args.pairs or wl["pairs"]
-    vals, last = [], None
-    for _ in range(args.warmup + args.steps):
-        last = cpu_reference_run(wl, npairs, max(2.0, min(args.cpu_seconds, 150.0 / (args.warmup + args.steps))),
-                                 threads, table)
-        vals.append(last)
-    timed = vals[args.warmup:]
-    secs = sum(v["seconds"] for v in timed)
-    cells = sum(v["cells"] for v in timed)
-    value = cells / secs / 1e9
-    line = {
-        "impl": "reference", "metric": "mar-mg Viterbi GCUPS (fill + traceback)", "value": value,
-        "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "pairs_per_s": sum(v["pairs"] for v in timed) / secs,
-        "config": {"workload": wl["desc"], "pairs_per_gpu": npairs, "k": wl["k"], "seed": wl["seed"],
-                   "note": "reference CPU path on host cores; each step = bounded stratified sample"},
-        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": last["cores"], "kind": last["kind"],
-                         "sample": last["sample"]},
-        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    emit(line)
-
-
-# ---------------------------------------------------------------------------------------------------
 def emit(line):
     """The JSON line is the LAST line of stdout: flush whatever C libraries (NCCL's version banner) still
     hold in their stdio buffers first."""
@@ -213,82 +143,234 @@ def emit(line):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+# CPU legs: the reference's own viterbi_mem + traceback_viterbi (oracle/_ref, else the C port), ONE PROCESS PER
+# CORE, each on its own contiguous block of the same seeded pair stream.
+def cpu_reference_run(wl, npairs_total, seconds, procs, table, first=0):
+    from tools import cpu_worker
+    est_gcups_core = 0.05
+    cells_per_pair = 338_000 if wl["id"] == 5 else 2_900_000
+    n = int(max(procs, min(npairs_total, seconds * est_gcups_core * 1e9 * procs / cells_per_pair)))
+    res = cpu_worker.run_pool(wl["id"], wl["seed"], first, n, table, float(G_OPEN), float(G_EXT), wl["k"], procs)
+    cells = sum(r["cells"] for r in res)
+    secs = max(r["seconds"] for r in res)         # all workers start together: the slowest one is the wall time
+    kind = res[0]["kind"]
+    return dict(value=cells / secs / 1e9, unit="GCUPS", cores=procs, kind=kind, seconds=secs, pairs=n,
+                pairs_per_s=n / secs, cells=cells,
+                sample=f"first {n} pairs of the seeded {wl['desc'].split(':')[0]} stream (i.i.d. length bins, "
+                       f"{cells:.3g} cells), viterbi_mem+traceback_viterbi, {procs} processes x 1 thread, -O3 -DNDEBUG")
+
+
+def run_reference(args, wl, table):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    npairs = args.pairs or wl["pairs"]
+    vals, last = [], None
+    for _ in range(args.warmup + args.steps):
+        last = cpu_reference_run(wl, npairs, max(2.0, min(args.cpu_seconds, 150.0 / (args.warmup + args.steps))),
+                                 procs, table)
+        vals.append(last)
+    timed = vals[args.warmup:]
+    secs = sum(v["seconds"] for v in timed)
+    cells = sum(v["cells"] for v in timed)
+    value = cells / secs / 1e9
+    line = {
+        "impl": "reference", "metric": "mar-mg Viterbi GCUPS (fill + traceback)", "value": value,
+        "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "pairs_per_s": sum(v["pairs"] for v in timed) / secs,
+        "config": {"workload": wl["desc"], "pairs": npairs, "k": wl["k"], "seed": wl["seed"]},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": last["cores"], "kind": last["kind"],
+                         "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference CPU path on host cores; each step = bounded sample of the workload",
+    }
+    emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------
+class Arena:
+    """One block of page-locked host memory carved into named uint8 arrays.  world == 1: cudaHostAlloc through
+    the library; world > 1: one file in /dev/shm mapped by every rank and registered with CUDA, so that all ranks
+    read the one input batch from, and deliver their rows to, the same physical memory."""
+
+    def __init__(self, sizes, world, rank, dist, lib):
+        self.lib, self.world, self.rank, self.path, self.pinned = lib, world, rank, None, True
+        self.off, total = {}, 0
+        for name, nbytes in sizes:
+            self.off[name] = (total, nbytes)
+            total += (nbytes + 4095) & ~4095
+        self.total = max(total, 4096)
+        if world == 1:
+            from coati_b200.capi import PinnedArena
+            self.block = PinnedArena(self.total)
+            self.buf = self.block.array
+        else:
+            import ctypes as C
+            name = [None]
+            if rank == 0:
+                name[0] = "/dev/shm/coati_bench_%s" % uuid.uuid4().hex
+                with open(name[0], "wb") as f:
+                    f.truncate(self.total)
+            dist.broadcast_object_list(name, src=0)
+            self.path = name[0]
+            self.buf = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.total,))
+            self.pinned = lib.coati_gpu_host_register(C.c_void_p(self.buf.ctypes.data), self.total) == 0
+
+    def view(self, name, dtype=np.uint8):
+        o, n = self.off[name]
+        return self.buf[o:o + n].view(dtype)
+
+    def close(self, dist):
+        if self.world == 1:
+            self.buf = None
+            self.block.free()
+            return
+        import ctypes as C
+        if self.pinned:
+            self.lib.coati_gpu_host_unregister(C.c_void_p(self.buf.ctypes.data))
+        dist.barrier()
+        if self.rank == 0:
+            os.unlink(self.path)
+
+
+def _fixed_alloc(bufs):
+    """alloc callback for synth_pairs that hands out the given arrays in order (a_all, b_all, anc_all, des_all)."""
+    it = iter(bufs)
+
+    def alloc(nbytes):
+        b = next(it)
+        assert len(b) >= nbytes
+        return b
+    return alloc
+
+
+def _compact_local(w, firsts, lasts):
+    """The pairs of the given ranges as one local CSR batch (for the device-resident metric)."""
+    a_off, b_off = w["a_off"], w["b_off"]
+    z = [np.zeros(0, np.uint64)]
+    la = np.concatenate([np.diff(a_off[int(f):int(l) + 1]) for f, l in zip(firsts, lasts)] or z)
+    lb = np.concatenate([np.diff(b_off[int(f):int(l) + 1]) for f, l in zip(firsts, lasts)] or z)
+    lo_a = np.zeros(len(la) + 1, np.uint64)
+    lo_b = np.zeros(len(lb) + 1, np.uint64)
+    np.cumsum(la, out=lo_a[1:])
+    np.cumsum(lb, out=lo_b[1:])
+
+    def cat(name, off):
+        parts = [w[name][int(off[int(f)]):int(off[int(l)])] for f, l in zip(firsts, lasts)]
+        return np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, np.uint8)
+    return dict(a_off=lo_a, b_off=lo_b, a_all=cat("a_all", a_off), b_all=cat("b_all", b_off),
+                anc_all=cat("anc_all", a_off), des_all=cat("des_all", b_off))
+
+
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
-    table = load_table(wl["table"])
     if args.impl == "reference":
-        run_reference(args, wl, table)
+        run_reference(args, wl, load_table(wl["table"]))
         return
 
     import torch
     import coati_b200
-    from coati_b200.capi import synth_pairs
+    from coati_b200 import capi
+    from synth import synth_offsets, synth_pairs
 
     rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        dist = None
-        torch.cuda.set_device(local)
-    npairs = args.pairs or wl["pairs"]
-    g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
-
-    # ---- synthetic batch in pinned host memory --------------------------------------------------
-    pinned = []
-
-    def alloc(nbytes):
-        t = torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True)
-        pinned.append(t)
-        return t.numpy()
-
-    t0 = time.perf_counter()
-    w = synth_pairs(npairs, wl["id"], wl["seed"], first=rank * npairs, alloc=alloc)
-    gen_s = time.perf_counter() - t0
-    la = np.diff(w["a_off"]).astype(np.float64)
-    lb = np.diff(w["b_off"]).astype(np.float64)
-    cells = float((la * lb).sum())
-    out_total = int(w["a_off"][-1] + w["b_off"][-1]) + npairs
-    out_a, out_b = alloc(out_total + 1), alloc(out_total + 1)
-    out_len = np.zeros(npairs, np.uint64)
-    score = np.zeros(npairs, np.float32)
-    status = np.zeros(npairs, np.int32)
+    strong = args.scaling == "strong"
+    npairs_arg = args.pairs or wl["pairs"]
+    npairs = npairs_arg if strong else npairs_arg * world      # pairs of the whole job
+    # the model: the product's own table builder (coati::set_subst), checked against the committed table
+    table = capi.host_marginal_table(**wl["model"])
+    want = load_table(wl["table"])
+    assert np.allclose(table, want, rtol=3e-5, atol=3e-6), "host table builder disagrees with tests/golden/tables.npz"
 
     ctx = coati_b200.Context(local)           # raises if the CUDA library/device is missing
-    ctx.set_model(table, g, e, wl["k"])
+    ctx.set_model(table, G_OPEN, G_EXT, wl["k"])
     info = ctx.device_info()
+    lib = ctx.lib
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    dev = torch.device("cuda", local)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident metric -----------------------------------------------------------------
-    batch = ctx.batch(w["a_off"], w["b_off"])
-    batch.upload(w["a_all"], w["b_all"], w["anc_all"], w["des_all"])
+    # ---- the one batch, in one page-locked arena ---------------------------------------------------------
+    t0 = time.perf_counter()
+    a_off, b_off = synth_offsets(npairs, wl["id"], wl["seed"], 0)
+    ta, tb = int(a_off[-1]), int(b_off[-1])
+    out_total = ta + tb + npairs
+    arena = Arena([("anc_all", ta + 1), ("des_all", tb + 1), ("a_all", ta + 1), ("b_all", tb + 1),
+                   ("out_a", out_total + 1), ("out_b", out_total + 1), ("out_len", 8 * npairs),
+                   ("score", 4 * npairs), ("status", 4 * npairs)], world, rank, dist, lib)
+    w = dict(a_off=a_off, b_off=b_off, anc_all=arena.view("anc_all"), des_all=arena.view("des_all"),
+             a_all=arena.view("a_all"), b_all=arena.view("b_all"))
+    if rank == 0:
+        synth_pairs(npairs, wl["id"], wl["seed"], 0,
+                    alloc=_fixed_alloc([w["a_all"], w["b_all"], w["anc_all"], w["des_all"]]))
+    out_a, out_b = arena.view("out_a"), arena.view("out_b")
+    out_len, score = arena.view("out_len", np.uint64), arena.view("score", np.float32)
+    status = arena.view("status", np.int32)
+    barrier()
+    gen_s = time.perf_counter() - t0
+
+    # ---- shards: contiguous chunks, heaviest first, greedy LPT over the ranks ------------------------------
+    if strong:
+        r_first, r_last, r_shard = capi.plan_shards(a_off, b_off, world)
+    else:  # weak: rank r owns pairs [r * P, (r + 1) * P)
+        r_first = np.arange(world, dtype=np.uint64) * np.uint64(npairs_arg)
+        r_last = r_first + np.uint64(npairs_arg)
+        r_shard = np.arange(world, dtype=np.uint32)
+    mine = np.flatnonzero(r_shard == rank)
+    my_first, my_last = r_first[mine], r_last[mine]
+    order = np.argsort(my_first)
+    cells_pair = np.diff(a_off).astype(np.float64) * np.diff(b_off).astype(np.float64)
+    cells_total = float(cells_pair.sum())
+    my_pairs = int((my_last - my_first).sum())
+    my_cells = float(sum(cells_pair[int(f):int(l)].sum() for f, l in zip(my_first, my_last)))
+
+    # ---- device-resident metric: the rank's pairs as one local CSR batch ----------------------------------
+    loc = _compact_local(w, my_first[order], my_last[order])
+    batch = ctx.batch(loc["a_off"], loc["b_off"])
+    batch.upload(loc["a_all"], loc["b_all"], loc["anc_all"], loc["des_all"])
     gather_bytes = 0
+    gather = None
     if dist is not None:
-        # result gather to rank 0 (the path's only collective): device-resident rows + per-pair records
         from coati_b200 import dist as cdist
         bufs = batch.device_buffers()
-        dev = torch.device("cuda", local)
         payload = {"out_a": cdist.DeviceBytes(bufs["out_a"], bufs["out_bytes"]).tensor(dev),
                    "out_b": cdist.DeviceBytes(bufs["out_b"], bufs["out_bytes"]).tensor(dev),
                    "results": cdist.DeviceBytes(bufs["results"], bufs["result_bytes"]).tensor(dev)}
-        recv_cache = {}
-        gather_bytes = 2 * bufs["out_bytes"] + bufs["result_bytes"]
+        gather = cdist.OverlappedGather(payload, stream, root=0)
+        gather_bytes = gather.bytes_to_root
 
-    def run_step():
+    fill_ms = trace_ms = compact_ms = 0.0
+
+    def run_step(timed):
+        nonlocal fill_ms, trace_ms, compact_ms
         batch.run()
-        if dist is not None:
-            with torch.cuda.stream(stream):
-                cdist.gather_to_root(payload, 0, recv_cache)
+        if gather is not None:
+            gather.step()
+        if timed:  # per-family device time of THIS step (synchronises the batch's stream, not the gather's)
+            tm = batch.timing()
+            fill_ms += tm["fill_ms"]
+            trace_ms += tm["traceback_ms"]
+            compact_ms += tm["compact_ms"]
 
     for _ in range(args.warmup):
-        run_step()
+        run_step(False)
+    if gather is not None:
+        gather.finish()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -296,32 +378,44 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    fill_ms = trace_ms = compact_ms = 0.0
     for _ in range(args.steps):
-        run_step()
+        run_step(True)
+    if gather is not None:
+        gather.finish()                        # the last step's gather is inside the timed region
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launches - launches0
-    tm = batch.timing()                        # per-family device time of the LAST step
-    fill_ms, trace_ms, compact_ms = tm["fill_ms"], tm["traceback_ms"], tm["compact_ms"]
+    fill_ms, trace_ms, compact_ms = fill_ms / args.steps, trace_ms / args.steps, compact_ms / args.steps
     stats = batch.stats()
     # check the batch ran clean before reporting anything
-    batch.download(out_a, out_b, out_len, score, status)
-    assert int((status != 0).sum()) == 0, "pairs failed"
-    assert int(out_len.min()) > 0
+    n_loc = len(loc["a_off"]) - 1
+    tot_loc = int(loc["a_off"][-1] + loc["b_off"][-1]) + n_loc + 1
+    chk = (np.zeros(tot_loc, np.uint8), np.zeros(tot_loc, np.uint8), np.zeros(n_loc, np.uint64),
+           np.zeros(n_loc, np.float32), np.zeros(n_loc, np.int32))
+    batch.download(*chk)
+    assert int((chk[4] != 0).sum()) == 0, "pairs failed"
+    assert n_loc == 0 or int(chk[2].min()) > 0
+    if gather is not None and rank == 0:
+        # the root holds every rank's result records (32 B: term[3], score, len, start, status, pad): all clean
+        torch.cuda.synchronize()
+        got_pairs = 0
+        for r, bufsr in enumerate(gather.root_buffers()):
+            rec = bufsr["results"].cpu().numpy().view(np.int32).reshape(-1, 8)
+            assert int((rec[:, 6] != 0).sum()) == 0 and (len(rec) == 0 or int(rec[:, 4].min()) > 0), f"rank {r} records"
+            got_pairs += len(rec)
+        assert got_pairs == npairs, "gather incomplete"
+    batch.destroy()
+    del loc, chk
 
-    # ---- end-to-end through the public C ABI with host buffers -----------------------------------
+    # ---- end-to-end through the public C ABI with host buffers ---------------------------------------------
+    outs = (out_a, out_b, out_len, score, status)
+
     def e2e_once():
         # the call a user makes: raw sequences in, aligned rows + scores out (marg_alignment semantics:
         # length checks, end-stop trim/restore, encoding on the device, Viterbi, traceback)
-        ctx._check(ctx.lib.coati_gpu_alignpair_batch(
-            ctx.h, npairs, w["anc_all"].ctypes.data, w["a_off"].ctypes.data_as(coati_b200.capi._u64p),
-            w["des_all"].ctypes.data, w["b_off"].ctypes.data_as(coati_b200.capi._u64p),
-            out_a.ctypes.data, out_b.ctypes.data, out_len.ctypes.data_as(coati_b200.capi._u64p),
-            score.ctypes.data_as(coati_b200.capi._fp), status.ctypes.data_as(coati_b200.capi._i32p)))
+        capi.alignpair_batch_ranges(ctx, w, outs, my_first, my_last)
 
-    batch.destroy()
     for _ in range(max(1, args.warmup)):         # warm-up (pool allocations, page faults)
         e2e_once()
     barrier()
@@ -330,88 +424,144 @@ def main():
     for _ in range(e2e_steps):
         e2e_once()
     torch.cuda.synchronize()
+    barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    assert int((status != 0).sum()) == 0 and int(out_len.min()) > 0, "e2e run failed"
-    h2d = int(w["a_off"][-1] + w["b_off"][-1])
-    d2h = int(2 * out_total + npairs * 32)
+    if rank == 0:  # every rank's rows are in the one arena
+        assert int((status != 0).sum()) == 0 and int(out_len.min()) > 0, "e2e run failed"
+    h2d = int(sum(int(a_off[int(l)] - a_off[int(f)]) + int(b_off[int(l)] - b_off[int(f)])
+                  for f, l in zip(my_first, my_last)))
+    d2h = int(2 * (h2d + my_pairs) + my_pairs * 32)
 
-    # ---- reduce over ranks ------------------------------------------------------------------------
+    # ---- reduce over ranks ------------------------------------------------------------------------------------
     if dist is not None:
-        t = torch.tensor([ms, e2e_s, fill_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, fill_ms_max = t.tolist()
-        c = torch.tensor([cells, float(npairs), float(launches)], dtype=torch.float64, device="cuda")
+        ms, e2e_s = t.tolist()
+        c = torch.tensor([float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        cells_all, pairs_all, launches_all = c.tolist()
+        launches_all, h2d_all, d2h_all = c.tolist()
+        per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+        per_rank[rank] = my_cells
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        shard_cells = per_rank.tolist()
     else:
-        cells_all, pairs_all, launches_all, fill_ms_max = cells, float(npairs), float(launches), fill_ms
+        launches_all, h2d_all, d2h_all, shard_cells = float(launches), float(h2d), float(d2h), [my_cells]
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = run_extras(ctx, capi, w, npairs, cells_total, outs, e2e_steps)
+    arena_pinned = arena.pinned
+    del w, outs, out_a, out_b, out_len, score, status
+    arena.close(dist)
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return
 
     secs = ms / 1e3
-    value = cells_all * args.steps / secs / 1e9
-    e2e_val = cells_all * e2e_steps / e2e_s / 1e9
-    # roofline of the dominant kernel (viterbi_pipe_kernel): FP32 issue, SURVEY 8(d)
+    value = cells_total * args.steps / secs / 1e9
+    e2e_val = cells_total * e2e_steps / e2e_s / 1e9
+    # roofline of the dominant kernel: FP32 issue; rank 0's shard, its own fill time
     sm_mhz = clocks.get("sm_mhz") or info["clock_khz"] / 1e3
     peak_tflops = info["sm_count"] * LANES_PER_SM * sm_mhz * 1e6 / 1e12
     peak_tflops_max = info["sm_count"] * LANES_PER_SM * (clocks.get("sm_max_mhz") or info["clock_khz"] / 1e3) * 1e6 / 1e12
-    ach_tflops = cells * FLOP_PER_CELL / (fill_ms / 1e3) / 1e12 if fill_ms > 0 else 0.0
+    ach_tflops = my_cells * FLOP_PER_CELL / (fill_ms / 1e3) / 1e12 if fill_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # DRAM bytes of the fill launches per step, from the committed ncu capture (bytes per cell there x cells here)
     traffic, traffic_note = None, None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh).get(args.workload, {})
         if "bytes_per_cell" in tj:
-            traffic = tj["bytes_per_cell"] * cells  # bytes per step, all fill launches of one GPU
-            traffic_note = ("DRAM bytes of the fill launches per step and GPU: %.4f B/cell measured by ncu --set full "
-                            "(profiles/r01_traffic.json) x cells; algorithmic decision stream 0.625 B/cell"
-                            % tj["bytes_per_cell"])
+            traffic = tj["bytes_per_cell"] * my_cells  # bytes per step, all fill launches of one GPU
+            traffic_note = ("DRAM bytes of the fill launches per step on rank 0: %.4f B/cell measured by ncu --set full "
+                            "(%s) x cells of the shard; algorithmic decision stream 0.625 B/cell"
+                            % (tj["bytes_per_cell"], tj.get("source", "profiles/")))
     except (OSError, ValueError):
         pass
     line = {
         "metric": "mar-mg Viterbi GCUPS (fill + traceback)", "value": value, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "pairs_per_s": pairs_all * args.steps / secs,
-        "config": {"workload": wl["desc"], "pairs_per_gpu": npairs, "k": wl["k"], "seed": wl["seed"],
-                   "cells_per_gpu": cells, "l2": "inputs + decision stream >> 126 MB L2 (no flush needed)",
-                   "decision_stream_bytes_per_gpu": stats["dir_bytes"], "chunks": stats["chunks"],
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "pairs_per_s": npairs * args.steps / secs,
+        "config": {"workload": wl["desc"], "pairs": npairs, "k": wl["k"], "seed": wl["seed"],
+                   "cells": cells_total, "l2": "inputs + decision stream >> 126 MB L2 (no flush needed)",
+                   "sharding": ("one batch; contiguous chunks, heaviest first, greedy LPT on sum(La*Lb) over ranks "
+                                "(coati_gpu_plan_shards)" if strong else "rank r owns pairs [r*P, (r+1)*P)"),
+                   "chunks": int(len(r_first)),
+                   "shard_cells_max_over_mean": max(shard_cells) / (sum(shard_cells) / world),
+                   "decision_stream_bytes_rank0": stats["dir_bytes"], "dir_chunks_rank0": stats["chunks"],
                    "gen_seconds": gen_s,
-                   "nccl_gather_bytes_per_rank_per_step": gather_bytes},
-        "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / e2e_steps, "pairs_per_s": pairs_all * e2e_steps / e2e_s,
-                "steps": e2e_steps},
+                   "host_arena": "cudaHostAlloc" if world == 1 else "/dev/shm + cudaHostRegister",
+                   "host_arena_pinned": bool(arena_pinned),
+                   "collective": None if dist is None else ("NCCL send/recv gather of rows + result records to rank 0, "
+                                                            "double-buffered staging copy, side stream"),
+                   "nccl_gather_bytes_to_root_per_step": gather_bytes},
+        "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "pairs_per_s": npairs * e2e_steps / e2e_s,
+                "steps": e2e_steps, "api": "coati_gpu_alignpair_batch_ranges, rows delivered to one host arena"},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
-        "roofline": {"bound": "fp32_issue", "kernel": "viterbi_pipe_kernel", "achieved": ach_tflops,
+        "roofline": {"bound": "fp32_issue", "kernel": wl["kernel"], "achieved": ach_tflops,
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops if peak_tflops else None,
                      "peak_at_max_clock": peak_tflops_max, "flop_per_cell": FLOP_PER_CELL,
-                     "kernel_ms_per_step": fill_ms, "kernel_gcups": cells / (fill_ms / 1e3) / 1e9 if fill_ms else None,
+                     "kernel_ms_per_step": fill_ms, "kernel_ms_note": "mean over the timed steps, rank 0's shard",
+                     "kernel_gcups": my_cells / (fill_ms / 1e3) / 1e9 if fill_ms else None,
                      "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": f"{info['sm_count']} SMs x 128 FP32 lanes x median SM clock under load",
                      "hbm_stream": {"achieved_gbs": stats["dir_bytes"] / (fill_ms / 1e3) / 1e9 if fill_ms else None,
                                     "peak_gbs": hbm_peak, "of": "measured" if peaks else "fallback"},
                      "traceback_ms_per_step": trace_ms, "compact_ms_per_step": compact_ms},
     }
+    if extra:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(
-                wl, npairs, args.cpu_seconds, os.cpu_count() or 1, table).items()
+                wl, npairs, args.cpu_seconds, os.cpu_count() or 1, want).items()
                 if k in ("value", "unit", "cores", "kind", "sample", "pairs_per_s")}
         except Exception as ex:  # the checker failing must not hide the measurement
             line["cpu_baseline"] = {"error": repr(ex)}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_extras(ctx, capi, w, npairs, cells_total, outs, e2e_steps):
+    """Driver-visible records beside the headline (N = 1 only): e2e from pageable host memory, and BASELINE
+    configs 1-4 (tools/bench_configs.py)."""
+    extra = {}
+    # (1) the same e2e call from PAGEABLE caller memory (what a C++ caller holding std::string / std::vector gets
+    #     unless it allocates with coati_gpu_host_alloc or registers its buffers)
+    try:
+        wp = dict(a_off=w["a_off"], b_off=w["b_off"], anc_all=np.array(w["anc_all"]), des_all=np.array(w["des_all"]))
+        po = (np.zeros(len(outs[0]), np.uint8), np.zeros(len(outs[1]), np.uint8), np.zeros(npairs, np.uint64),
+              np.zeros(npairs, np.float32), np.zeros(npairs, np.int32))
+        f = np.array([0], np.uint64)
+        l = np.array([npairs], np.uint64)
+        capi.alignpair_batch_ranges(ctx, wp, po, f, l)
+        t0 = time.perf_counter()
+        steps = min(2, e2e_steps)
+        for _ in range(steps):
+            capi.alignpair_batch_ranges(ctx, wp, po, f, l)
+        dt = time.perf_counter() - t0
+        assert int((po[4] != 0).sum()) == 0
+        extra["e2e_pageable"] = {"value": cells_total * steps / dt / 1e9, "unit": "GCUPS", "ms_per_step": 1e3 * dt / steps,
+                                 "note": "same call, caller arenas in pageable memory (numpy): copies are staged by the driver"}
+        del wp, po
+    except Exception as ex:
+        extra["e2e_pageable"] = {"error": repr(ex)}
+    # (2) BASELINE configs 1-4
+    try:
+        from tools import bench_configs
+        extra["configs"] = bench_configs.collect(ctx)
+    except Exception as ex:
+        extra["configs"] = {"error": repr(ex)}
+    return extra
 
 
 if __name__ == "__main__":

@@ -59,6 +59,19 @@ def load_library() -> C.CDLL:
     lib.coati_gpu_viterbi_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, vp, vp,
                                             _u64p, _fp, _i32p]
     lib.coati_gpu_alignpair_batch.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, _u64p, _fp, _i32p]
+    lib.coati_gpu_multi_alignpair_batch.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp,
+                                                    _u64p, _fp, _i32p]
+    lib.coati_gpu_plan_shards.argtypes = [C.c_size_t, _u64p, _u64p, C.c_uint32, C.c_size_t, _u64p, _u64p,
+                                          C.POINTER(C.c_uint32)]
+    lib.coati_gpu_plan_shards.restype = C.c_size_t
+    lib.coati_gpu_alignpair_batch_ranges.argtypes = [vp, C.c_size_t, vp, _u64p, vp, _u64p, vp, vp, _u64p, _fp, _i32p,
+                                                     C.c_size_t, _u64p, _u64p]
+    lib.coati_gpu_host_alloc.argtypes = [C.c_size_t]
+    lib.coati_gpu_host_alloc.restype = vp
+    lib.coati_gpu_host_free.argtypes = [vp]
+    lib.coati_gpu_host_free.restype = None
+    lib.coati_gpu_host_register.argtypes = [vp, C.c_size_t]
+    lib.coati_gpu_host_unregister.argtypes = [vp]
     lib.coati_gpu_batch_create.argtypes = [vp, C.c_size_t, _u64p, _u64p, C.POINTER(vp)]
     lib.coati_gpu_batch_upload.argtypes = [vp, vp, vp, vp, vp]
     lib.coati_gpu_batch_run.argtypes = [vp]
@@ -68,12 +81,6 @@ def load_library() -> C.CDLL:
                                            C.POINTER(C.c_double), _u64p]
     lib.coati_gpu_batch_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), _u64p,
                                                    C.POINTER(vp), _u64p]
-    lib.coati_synth_offsets.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
-                                        C.c_double, C.c_int, _u64p, _u64p]
-    lib.coati_synth_offsets.restype = None
-    lib.coati_synth_fill.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
-                                     C.c_double, C.c_int, _u64p, _u64p, vp, vp, vp, vp]
-    lib.coati_synth_fill.restype = None
     lib.coati_gpu_batch_destroy.argtypes = [vp]
     lib.coati_gpu_batch_destroy.restype = None
     # host layer (no GPU): table builder, encoding, seeding, re-scoring
@@ -456,24 +463,65 @@ class Context:
         return d, np.float32(score.value)
 
 
-def synth_pairs(n: int, workload: int = 5, seed: int = 42, first: int = 0, sub: float = 0.05,
-                indel: float = 0.005, threads: int = 0, alloc=None):
-    """Seeded synthetic pairs.  Returns dict(a_off, b_off, a_all, b_all, anc_all,
-    des_all); `alloc(nbytes)` may supply pinned uint8 buffers."""
+def plan_shards(a_off, b_off, n_shards: int):
+    """coati_gpu_plan_shards: contiguous chunks of one CSR batch, heaviest first, given to shards by greedy
+    longest-processing-time.  Returns (first, last, shard) arrays, one entry per chunk."""
     lib = load_library()
-    threads = threads or (os.cpu_count() or 1)
-    a_off = np.zeros(n + 1, dtype=np.uint64)
-    b_off = np.zeros(n + 1, dtype=np.uint64)
-    lib.coati_synth_offsets(seed, first, n, workload, sub, indel, threads, a_off.ctypes.data_as(_u64p),
-                            b_off.ctypes.data_as(_u64p))
-    alloc = alloc or (lambda nbytes: np.zeros(nbytes, dtype=np.uint8))
-    ta, tb = int(a_off[-1]), int(b_off[-1])
-    out = dict(a_off=a_off, b_off=b_off, a_all=alloc(ta + 1), b_all=alloc(tb + 1), anc_all=alloc(ta + 1),
-               des_all=alloc(tb + 1))
-    lib.coati_synth_fill(seed, first, n, workload, sub, indel, threads, a_off.ctypes.data_as(_u64p),
-                         b_off.ctypes.data_as(_u64p), _vp(out["anc_all"]), _vp(out["des_all"]),
-                         _vp(out["a_all"]), _vp(out["b_all"]))
-    return out
+    a_off = np.ascontiguousarray(a_off, dtype=np.uint64)
+    b_off = np.ascontiguousarray(b_off, dtype=np.uint64)
+    npairs = len(a_off) - 1
+    cap = 2 * (npairs // 8192 + n_shards + 2)
+    first = np.zeros(cap, dtype=np.uint64)
+    last = np.zeros(cap, dtype=np.uint64)
+    shard = np.zeros(cap, dtype=np.uint32)
+    n = lib.coati_gpu_plan_shards(npairs, a_off.ctypes.data_as(_u64p), b_off.ctypes.data_as(_u64p), n_shards, cap,
+                                  first.ctypes.data_as(_u64p), last.ctypes.data_as(_u64p),
+                                  shard.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if n == 0 and npairs:
+        raise RuntimeError("coati_gpu_plan_shards failed")
+    return first[:n].copy(), last[:n].copy(), shard[:n].copy()
+
+
+def alignpair_batch_ranges(ctx: "Context", w, outs, first, last):
+    """coati_gpu_alignpair_batch_ranges on the CSR batch `w` (dict of a_off, b_off, anc_all, des_all) into
+    outs = (out_a, out_b, out_len, score, status)."""
+    out_a, out_b, out_len, score, status = outs
+    first = np.ascontiguousarray(first, dtype=np.uint64)
+    last = np.ascontiguousarray(last, dtype=np.uint64)
+    ctx._check(ctx.lib.coati_gpu_alignpair_batch_ranges(
+        ctx.h, len(w["a_off"]) - 1, _vp(w["anc_all"]), w["a_off"].ctypes.data_as(_u64p), _vp(w["des_all"]),
+        w["b_off"].ctypes.data_as(_u64p), _vp(out_a), _vp(out_b), out_len.ctypes.data_as(_u64p),
+        score.ctypes.data_as(_fp), status.ctypes.data_as(_i32p), len(first), first.ctypes.data_as(_u64p),
+        last.ctypes.data_as(_u64p)))
+
+
+def multi_alignpair_batch(ctxs, w, outs):
+    """coati_gpu_multi_alignpair_batch: one CSR batch over several contexts (one per device)."""
+    out_a, out_b, out_len, score, status = outs
+    lib = ctxs[0].lib
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    ctxs[0]._check(lib.coati_gpu_multi_alignpair_batch(
+        arr, len(ctxs), len(w["a_off"]) - 1, _vp(w["anc_all"]), w["a_off"].ctypes.data_as(_u64p), _vp(w["des_all"]),
+        w["b_off"].ctypes.data_as(_u64p), _vp(out_a), _vp(out_b), out_len.ctypes.data_as(_u64p),
+        score.ctypes.data_as(_fp), status.ctypes.data_as(_i32p)))
+
+
+class PinnedArena:
+    """uint8 numpy view of page-locked host memory from coati_gpu_host_alloc."""
+
+    def __init__(self, nbytes: int):
+        self.lib = load_library()
+        self.nbytes = max(1, int(nbytes))
+        self.ptr = self.lib.coati_gpu_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("coati_gpu_host_alloc failed")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.coati_gpu_host_free(self.ptr)
+            self.ptr = None
 
 
 # ---- host layer helpers (C++ table builder / sequence prep behind coati_host_* entry points) ---------

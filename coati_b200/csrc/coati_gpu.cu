@@ -15,6 +15,7 @@
 #include <new>
 #include <string>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -1121,7 +1122,7 @@ extern "C" void coati_gpu_batch_destroy(coati_gpu_batch* bt) {
 
 // process_marginal's length checks (before trimming, utils.cc:819-837) and trim_end_stops
 // (utils.cc:945-967 via cod_int) for the raw pairs [p0, p1): bit 7 = bad length, bit 0 / 1 = the
-// ancestor / descendant ends with a stop codon.
+// ancestor / descendant ends with a stop codon; raw[p - p0] for pair p.
 static void scan_raw_pairs(uint32_t k, const char* anc_all, const uint64_t* anc_off, const char* des_all,
                            const uint64_t* des_off, size_t p0, size_t p1, uint8_t* raw) {
     auto nuc = [](char ch) -> int {
@@ -1146,15 +1147,91 @@ static void scan_raw_pairs(uint32_t k, const char* anc_all, const uint64_t* anc_
         if(la % 3 != 0 || la % k != 0 || lb % k != 0) f |= 0x80;
         if(ends_with_stop(anc_all + anc_off[p], la)) f |= 1;
         if(ends_with_stop(des_all + des_off[p], lb)) f |= 2;
-        raw[p] = f;
+        raw[p - p0] = f;
     }
 }
 
-static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
-                                  const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
-                                  const char* anc_all, const char* des_all, char* out_a, char* out_b,
-                                  uint64_t* out_len, float* score, int32_t* status, bool raw_mode,
-                                  const uint32_t* model, size_t nsub);
+// ---------------------------------------------------------------------------------------------
+// One CSR batch as a queue of contiguous sub-batches.  A context's worker takes the next range whenever one
+// of its three pipeline lanes is free; several workers (one per device) may share one queue, which is the
+// whole multi-GPU scheduler: pairs are independent, ranges are handed out heaviest first
+// (longest-processing-time order on the sum of La * Lb), and a device that finishes early simply takes more.
+struct BatchArgs {
+    size_t npairs;
+    const uint8_t* a_all;
+    const uint64_t* a_off;
+    const uint8_t* b_all;
+    const uint64_t* b_off;
+    const char* anc_all;
+    const char* des_all;
+    char* out_a;
+    char* out_b;
+    uint64_t* out_len;
+    float* score;
+    int32_t* status;
+    bool raw_mode;
+    const uint32_t* model;
+};
+
+struct RangeQueue {
+    std::vector<std::pair<size_t, size_t>> ranges;  // [first, last) in pair indices
+    std::atomic<size_t> next{0};
+    std::atomic<bool> abort{false};
+    uint64_t max_sym = 0;    // symbols (a + b) of the biggest range
+    size_t max_pairs = 0;
+    bool pop(size_t& p0, size_t& p1) {
+        if(abort.load(std::memory_order_relaxed)) return false;
+        const size_t j = next.fetch_add(1, std::memory_order_relaxed);
+        if(j >= ranges.size()) return false;
+        p0 = ranges[j].first, p1 = ranges[j].second;
+        return true;
+    }
+    void add(size_t p0, size_t p1, const uint64_t* a_off, const uint64_t* b_off) {
+        ranges.emplace_back(p0, p1);
+        max_sym = std::max<uint64_t>(max_sym, (a_off[p1] - a_off[p0]) + (b_off[p1] - b_off[p0]));
+        max_pairs = std::max(max_pairs, p1 - p0);
+    }
+};
+
+// lattice cells of pairs [p0, p1): the cost the ranges are balanced on
+static double range_cells(const uint64_t* a_off, const uint64_t* b_off, size_t p0, size_t p1) {
+    double c = 0;
+    for(size_t p = p0; p < p1; ++p) c += (double)(a_off[p + 1] - a_off[p]) * (double)(b_off[p + 1] - b_off[p]);
+    return c;
+}
+
+// Cut [0, npairs) into contiguous chunks of equal WEIGHT (sum of La * Lb): about npairs / chunk of them, rounded
+// up to a multiple of `multiple` so that they divide evenly over that many workers, and none with more than four
+// times `chunk` pairs (a batch sorted by length would otherwise put millions of short pairs into one chunk).
+// Returned heaviest first.
+static void plan_chunks(size_t npairs, const uint64_t* a_off, const uint64_t* b_off, size_t chunk, size_t multiple,
+                        std::vector<std::pair<size_t, size_t>>& out, std::vector<double>& cost) {
+    size_t n = std::max<size_t>(1, (npairs + chunk - 1) / chunk);
+    if(multiple > 1 && n > 1) n = std::min(std::max<size_t>(npairs, 1), (n + multiple - 1) / multiple * multiple);
+    const double total = range_cells(a_off, b_off, 0, npairs);
+    std::vector<std::pair<size_t, size_t>> r;
+    std::vector<double> c;
+    size_t p0 = 0;
+    double acc = 0, done = 0;
+    for(size_t p = 0; p < npairs; ++p) {
+        acc += (double)(a_off[p + 1] - a_off[p]) * (double)(b_off[p + 1] - b_off[p]);
+        // the k-th cut sits where the running weight passes k / n of the total
+        const bool heavy = done + acc >= total * (double)(r.size() + 1) / (double)n;
+        if(p + 1 == npairs || ((heavy || p + 1 - p0 >= 4 * chunk) && npairs - (p + 1) >= 1)) {
+            r.emplace_back(p0, p + 1);
+            c.push_back(acc);
+            done += acc, acc = 0, p0 = p + 1;
+        }
+    }
+    if(r.empty()) r.emplace_back(0, npairs), c.push_back(0.0);
+    std::vector<size_t> order(r.size());
+    for(size_t j = 0; j < r.size(); ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return c[x] > c[y]; });
+    out.clear(), cost.clear();
+    for(size_t j : order) out.push_back(r[j]), cost.push_back(c[j]);
+}
+
+static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQueue& q, bool pipelined);
 
 static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
                               const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
@@ -1170,8 +1247,16 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
     if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(16, npairs / kMinPipe);
     if(const char* env = std::getenv("COATI_GPU_NSUB")) nsub = std::max(1, std::atoi(env));  // tuning
     if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
-    int rc = viterbi_batch_pipeline(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
-                                    out_len, score, status, raw_mode, model, nsub);
+    const BatchArgs A{npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b, out_len, score, status,
+                      raw_mode, model};
+    const uint64_t zero_off[1] = {0};
+    auto run = [&](size_t parts) {
+        RangeQueue q;
+        for(size_t j = 0; j < parts; ++j)  // in input order: a single device gains nothing from reordering
+            q.add(npairs * j / parts, npairs * (j + 1) / parts, npairs ? a_off : zero_off, npairs ? b_off : zero_off);
+        return viterbi_batch_pipeline(ctx, A, q, parts > 1);
+    };
+    int rc = run(nsub);
     if(rc == COATI_GPU_E_NOMEM) {
         // a lane owns a third of the memory: a pair too big for that may still fit the whole device; and
         // idle pool blocks of earlier calls are given back before the plan is redone from the memory
@@ -1179,40 +1264,28 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
         CU_TRY(ctx, cudaSetDevice(ctx->device));
         CU_TRY(ctx, cudaDeviceSynchronize());
         ctx->pool.trim();
-        rc = viterbi_batch_pipeline(ctx, npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b,
-                                    out_len, score, status, raw_mode, model, 1);
+        rc = run(1);
     }
     return rc;
 }
 
-static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
-                                  const uint64_t* a_off, const uint8_t* b_all, const uint64_t* b_off,
-                                  const char* anc_all, const char* des_all, char* out_a, char* out_b,
-                                  uint64_t* out_len, float* score, int32_t* status, bool raw_mode,
-                                  const uint32_t* model, size_t nsub) {
-    // raw pairs: the per-pair scan runs sub-batch by sub-batch, inside the pipeline
-    std::vector<uint8_t> rawbuf;
-    if(raw_mode) {
-        try {
-            rawbuf.resize(npairs);
-        } catch(const std::bad_alloc&) {
-            return COATI_GPU_E_NOMEM;
-        }
-    }
-    const uint8_t* raw = raw_mode ? rawbuf.data() : nullptr;
+static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQueue& q, bool pipelined) {
+    const size_t npairs = A.npairs;
+    const uint64_t *a_off = A.a_off, *b_off = A.b_off;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
     constexpr int NSLOT = 3;  // sub-batches in flight: one finishing, one filling, one queued behind it
     coati_gpu_batch* bt[NSLOT] = {nullptr, nullptr, nullptr};
     size_t first[NSLOT] = {0, 0, 0};
     static_assert(NSLOT == coati_gpu_ctx::NLANE, "one lane per slot");
+    // raw pairs: the per-pair scan (length checks, end stops) runs range by range, inside the pipeline
+    std::vector<uint8_t> rawbuf;
     // direction-stream budget of a lane, from the memory free now (the GPU is idle: cheap call)
     uint64_t lane_budget = 0;
-    if(nsub > 1) {
+    if(pipelined) {
         size_t free_b = 0;
-        CU_TRY(ctx, cudaSetDevice(ctx->device));
         CU_TRY(ctx, ctx->free_bytes(&free_b));
         free_b += ctx->pool.idle_bytes();
-        const uint64_t sym = (a_off[npairs] - a_off[0]) + (b_off[npairs] - b_off[0]);
-        const uint64_t fixed_sub = (4 * sym + npairs * (2 + sizeof(PairDesc) + sizeof(PairResult))) / nsub * 5 / 4 +
+        const uint64_t fixed_sub = (4 * q.max_sym + q.max_pairs * (2 + sizeof(PairDesc) + sizeof(PairResult))) * 5 / 4 +
                                    (256ull << 20);
         lane_budget = free_b > NSLOT * fixed_sub
                           ? static_cast<uint64_t>((free_b - NSLOT * fixed_sub) * 0.85 / NSLOT) : (1ull << 20);
@@ -1231,9 +1304,9 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, size_t npairs, const uint8
         }
         for(size_t p = 0; rc == COATI_GPU_OK && p < b->npairs; ++p) {
             const PairResult& r = b->h_results[p];
-            if(out_len) out_len[first[slot] + p] = r.len;
-            if(score) score[first[slot] + p] = r.score;
-            if(status) status[first[slot] + p] = r.status;
+            if(A.out_len) A.out_len[first[slot] + p] = r.len;
+            if(A.score) A.score[first[slot] + p] = r.score;
+            if(A.status) A.status[first[slot] + p] = r.status;
         }
         if(trace && rc == COATI_GPU_OK) {
             double fill = 0, tb = 0, ex = 0;
@@ -1246,33 +1319,43 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, size_t npairs, const uint8
         return rc;
     };
     int rc = COATI_GPU_OK;
-    for(size_t j = 0; j < nsub && rc == COATI_GPU_OK; ++j) {
+    size_t p0 = 0, p1 = 0;
+    for(size_t j = 0; rc == COATI_GPU_OK && q.pop(p0, p1); ++j) {
         const int slot = (int)(j % NSLOT);
         rc = finish(slot);
         if(rc != COATI_GPU_OK) break;
-        const size_t p0 = npairs * j / nsub, p1 = npairs * (j + 1) / nsub;
         first[slot] = p0;
         mark("plan begin", p0);
-        if(raw_mode) scan_raw_pairs(ctx->gap.k, anc_all, a_off, des_all, b_off, p0, p1, rawbuf.data());
-        rc = batch_create_on(ctx, nsub > 1 ? ctx->lane_hi[slot] : ctx->stream,
-                             nsub > 1 ? ctx->lane_fill[slot] : ctx->stream, lane_budget, p1 - p0,
-                             a_off + p0, b_off + p0, &bt[slot], raw ? raw + p0 : nullptr,
-                             model ? model + p0 : nullptr);
+        const uint8_t* raw = nullptr;
+        if(A.raw_mode) {
+            try {
+                rawbuf.resize(p1 - p0);
+            } catch(const std::bad_alloc&) {
+                rc = COATI_GPU_E_NOMEM;
+                break;
+            }
+            scan_raw_pairs(ctx->gap.k, A.anc_all, a_off, A.des_all, b_off, p0, p1, rawbuf.data());
+            raw = rawbuf.data();
+        }
+        rc = batch_create_on(ctx, pipelined ? ctx->lane_hi[slot] : ctx->stream,
+                             pipelined ? ctx->lane_fill[slot] : ctx->stream, lane_budget, p1 - p0,
+                             a_off + p0, b_off + p0, &bt[slot], raw, A.model ? A.model + p0 : nullptr);
         if(rc != COATI_GPU_OK) break;
         mark("plan end", p0);
         const uint64_t ao = npairs ? a_off[p0] : 0, bo = npairs ? b_off[p0] : 0;
-        rc = coati_gpu_batch_upload(bt[slot], a_all ? a_all + ao : nullptr, b_all ? b_all + bo : nullptr,
-                                    anc_all ? anc_all + ao : nullptr, des_all ? des_all + bo : nullptr);
+        rc = coati_gpu_batch_upload(bt[slot], A.a_all ? A.a_all + ao : nullptr, A.b_all ? A.b_all + bo : nullptr,
+                                    A.anc_all ? A.anc_all + ao : nullptr, A.des_all ? A.des_all + bo : nullptr);
         mark("upload enqueued", p0);
         if(rc == COATI_GPU_OK) rc = coati_gpu_batch_run(bt[slot]);
         mark("run enqueued", p0);
         if(rc == COATI_GPU_OK)
-            rc = batch_download_async(bt[slot], out_a ? out_a + ao + bo + p0 : nullptr,
-                                      out_b ? out_b + ao + bo + p0 : nullptr);
+            rc = batch_download_async(bt[slot], A.out_a ? A.out_a + ao + bo + p0 : nullptr,
+                                      A.out_b ? A.out_b + ao + bo + p0 : nullptr);
         mark("download enqueued", p0);
     }
-    for(size_t j = nsub; j < nsub + NSLOT; ++j) {  // oldest first
-        const int r2 = finish((int)(j % NSLOT));
+    if(rc != COATI_GPU_OK) q.abort.store(true);
+    for(int sl = 0; sl < NSLOT; ++sl) {
+        const int r2 = finish(sl);
         if(rc == COATI_GPU_OK) rc = r2;
     }
     return rc;
@@ -1311,6 +1394,128 @@ extern "C" int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, cons
     if(!ctx->model_set) return COATI_GPU_E_ARG;
     return viterbi_batch_impl(ctx, npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b,
                               out_len, score, status, true);
+}
+
+// ---- one batch over several devices ------------------------------------------------------------------
+// north_star (4) / SURVEY 8(e): independent pairs sharded over the GPUs of one box by length-binned work
+// queues.  The batch is cut into contiguous chunks, ordered heaviest first, and one host thread per context
+// runs the three-lane pipeline of the single-device call on whatever chunk it pops next; inside a chunk the
+// planner bins the pairs by kernel configuration and lattice size as always.  Results land in the caller's
+// arenas in input order -- no collective, no second copy.
+static size_t multi_chunk_pairs(size_t npairs, size_t n_workers) {
+    // about eight chunks per device keep the tail short; 8192 pairs still fill a B200 for a fill launch
+    const size_t want = npairs / std::max<size_t>(1, 8 * n_workers);
+    return std::min<size_t>(32768, std::max<size_t>(8192, want));
+}
+
+extern "C" int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n_ctx, size_t npairs,
+                                               const char* anc_all, const uint64_t* anc_off,
+                                               const char* des_all, const uint64_t* des_off, char* out_a,
+                                               char* out_b, uint64_t* out_len, float* score, int32_t* status) {
+    if(!ctxs || n_ctx < 1 || (npairs && (!anc_off || !des_off || !anc_all || !des_all))) return COATI_GPU_E_ARG;
+    for(int i = 0; i < n_ctx; ++i) {
+        if(!ctxs[i] || !ctxs[i]->model_set) return COATI_GPU_E_ARG;
+        // one model for the whole batch: same gap constants everywhere (the tables are the caller's word)
+        if(std::memcmp(&ctxs[i]->gap, &ctxs[0]->gap, sizeof(GapConsts)) != 0) return COATI_GPU_E_ARG;
+        for(int j = 0; j < i; ++j)
+            if(ctxs[j] == ctxs[i]) return COATI_GPU_E_ARG;
+    }
+    if(n_ctx == 1 || npairs < 2 * 8192)
+        return coati_gpu_alignpair_batch(ctxs[0], npairs, anc_all, anc_off, des_all, des_off, out_a, out_b, out_len,
+                                         score, status);
+    const BatchArgs A{npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b, out_len, score,
+                      status, true, nullptr};
+    RangeQueue q;
+    try {
+        std::vector<std::pair<size_t, size_t>> chunks;
+        std::vector<double> cost;
+        plan_chunks(npairs, anc_off, des_off, multi_chunk_pairs(npairs, (size_t)n_ctx), (size_t)n_ctx, chunks, cost);
+        for(const auto& c : chunks) q.add(c.first, c.second, anc_off, des_off);
+    } catch(const std::bad_alloc&) {
+        return COATI_GPU_E_NOMEM;
+    }
+    std::vector<int> rcs((size_t)n_ctx, COATI_GPU_OK);
+    std::vector<std::thread> workers;
+    for(int i = 1; i < n_ctx; ++i)
+        workers.emplace_back([&, i] { rcs[(size_t)i] = viterbi_batch_pipeline(ctxs[i], A, q, true); });
+    rcs[0] = viterbi_batch_pipeline(ctxs[0], A, q, true);  // the calling thread drives the first device
+    for(std::thread& t : workers) t.join();
+    for(int rc : rcs)
+        if(rc != COATI_GPU_OK) return rc;
+    return COATI_GPU_OK;
+}
+
+// The same plan for callers that run one PROCESS per device (bench.py under torchrun): contiguous chunks,
+// heaviest first, each given to the least-loaded shard (greedy longest-processing-time); every process
+// computes the identical plan from the offsets alone.  Returns the number of ranges written (<= max_ranges;
+// 0 if the arrays are too small).
+extern "C" size_t coati_gpu_plan_shards(size_t npairs, const uint64_t* a_off, const uint64_t* b_off,
+                                        uint32_t n_shards, size_t max_ranges, uint64_t* range_first,
+                                        uint64_t* range_last, uint32_t* range_shard) {
+    if(!a_off || !b_off || n_shards == 0 || !range_first || !range_last || !range_shard) return 0;
+    std::vector<std::pair<size_t, size_t>> chunks;
+    std::vector<double> cost;
+    plan_chunks(npairs, a_off, b_off, multi_chunk_pairs(npairs, n_shards), n_shards, chunks, cost);
+    if(chunks.size() > max_ranges) return 0;
+    std::vector<double> load(n_shards, 0.0);
+    for(size_t j = 0; j < chunks.size(); ++j) {
+        const uint32_t sh = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[sh] += cost[j];
+        range_first[j] = chunks[j].first, range_last[j] = chunks[j].second, range_shard[j] = sh;
+    }
+    return chunks.size();
+}
+
+// alignpair for the ranges [first[j], last[j]) of one CSR batch (a shard of coati_gpu_plan_shards): inputs and
+// outputs are addressed exactly as in coati_gpu_alignpair_batch, pairs outside the ranges are not touched.
+extern "C" int coati_gpu_alignpair_batch_ranges(coati_gpu_ctx* ctx, size_t npairs, const char* anc_all,
+                                                const uint64_t* anc_off, const char* des_all,
+                                                const uint64_t* des_off, char* out_a, char* out_b,
+                                                uint64_t* out_len, float* score, int32_t* status, size_t n_ranges,
+                                                const uint64_t* first, const uint64_t* last) {
+    if(!ctx || !ctx->model_set || (npairs && (!anc_off || !des_off || !anc_all || !des_all))) return COATI_GPU_E_ARG;
+    if(n_ranges && (!first || !last)) return COATI_GPU_E_ARG;
+    const BatchArgs A{npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b, out_len, score,
+                      status, true, nullptr};
+    RangeQueue q;
+    for(size_t j = 0; j < n_ranges; ++j) {
+        if(first[j] > last[j] || last[j] > npairs) return COATI_GPU_E_ARG;
+        if(first[j] < last[j]) q.add(first[j], last[j], anc_off, des_off);
+    }
+    if(q.ranges.empty()) return COATI_GPU_OK;
+    return viterbi_batch_pipeline(ctx, A, q, true);
+}
+
+// ---- pinned host memory for callers --------------------------------------------------------------------
+// The pipelined calls overlap H2D, kernels and D2H only when the caller's arenas are page-locked (a copy
+// from or to pageable memory is staged by the driver and blocks the issuing thread).  A C++ caller holding
+// std::string / std::vector either allocates its arenas here or registers them once.
+extern "C" void* coati_gpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void coati_gpu_host_free(void* p) {
+    if(p) cudaFreeHost(p);
+}
+extern "C" int coati_gpu_host_register(void* p, size_t bytes) {
+    if(!p || !bytes) return COATI_GPU_E_ARG;
+    if(cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return COATI_GPU_E_CUDA;
+    }
+    return COATI_GPU_OK;
+}
+extern "C" int coati_gpu_host_unregister(void* p) {
+    if(!p) return COATI_GPU_E_ARG;
+    if(cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return COATI_GPU_E_CUDA;
+    }
+    return COATI_GPU_OK;
 }
 
 extern "C" int coati_gpu_viterbi(coati_gpu_ctx* ctx, const uint8_t* a, size_t La, const uint8_t* b,

@@ -105,6 +105,35 @@ int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, const char* anc
                               char* out_a, char* out_b, uint64_t* out_len, float* score,
                               int32_t* status);
 
+/* ---- the same call over several GPUs of one box (north_star (4)) ----------------------------
+ * The reference is single-threaded and has no analogue; its natural batch client is the per-leaf loop of
+ * align_msa.cc:285-318.  ctxs: one context per device, all with the same model set.  The batch is cut into
+ * contiguous chunks, ordered heaviest first (longest-processing-time on the sum of La * Lb), and one host
+ * thread per context pipelines whatever chunk it pops next from the shared queue; results land in the
+ * caller's arenas in input order, exactly as coati_gpu_alignpair_batch leaves them (no collective). */
+int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n_ctx, size_t npairs, const char* anc_all,
+                                    const uint64_t* anc_off, const char* des_all, const uint64_t* des_off,
+                                    char* out_a, char* out_b, uint64_t* out_len, float* score,
+                                    int32_t* status);
+/* For callers that run one PROCESS per device: the same chunks given to n_shards shards by greedy
+ * longest-processing-time (deterministic: every process computes the same plan from the offsets), and the
+ * alignpair call restricted to a shard's ranges [first[j], last[j]) of the one CSR batch.  plan_shards
+ * returns the number of ranges written, 0 if max_ranges is too small (2 * (npairs / 8192 + n_shards + 2) always suffices). */
+size_t coati_gpu_plan_shards(size_t npairs, const uint64_t* a_off, const uint64_t* b_off, uint32_t n_shards,
+                             size_t max_ranges, uint64_t* range_first, uint64_t* range_last,
+                             uint32_t* range_shard);
+int coati_gpu_alignpair_batch_ranges(coati_gpu_ctx* ctx, size_t npairs, const char* anc_all,
+                                     const uint64_t* anc_off, const char* des_all, const uint64_t* des_off,
+                                     char* out_a, char* out_b, uint64_t* out_len, float* score, int32_t* status,
+                                     size_t n_ranges, const uint64_t* first, const uint64_t* last);
+
+/* Page-locked host memory for the arenas of the batch calls (they overlap copies and kernels only from and
+ * to pinned memory): allocate here, or register memory the caller already owns. */
+void* coati_gpu_host_alloc(size_t bytes);
+void coati_gpu_host_free(void* p);
+int coati_gpu_host_register(void* p, size_t bytes);
+int coati_gpu_host_unregister(void* p);
+
 /* Staged form of the same call, so the device-resident part can be timed alone:
  *   create  : host-side plan (length-binned LPT order, direction-buffer chunks) + device buffers
  *   upload  : H2D of sequences        run : fill + traceback kernels only (async on the stream)
@@ -132,15 +161,6 @@ int coati_gpu_batch_timing(coati_gpu_batch* batch, double* fill_ms, double* trac
 int coati_gpu_batch_device_buffers(coati_gpu_batch* batch, void** out_a, void** out_b,
                                    uint64_t* out_bytes, void** results, uint64_t* result_bytes);
 void coati_gpu_batch_destroy(coati_gpu_batch* batch);
-
-/* ---- host utilities (no GPU involved) ---------------------------------------------------------
- * Seeded synthetic workloads of SURVEY.md 8(d): workload 5 = length-binned C5 pairs, 4 = C4
- * (300-3000 nt).  Pair p depends only on (seed, first + p).  offsets: n + 1 entries each. */
-void coati_synth_offsets(uint64_t seed, uint64_t first, uint64_t n, int workload, double sub,
-                         double indel, int threads, uint64_t* a_off, uint64_t* b_off);
-void coati_synth_fill(uint64_t seed, uint64_t first, uint64_t n, int workload, double sub,
-                      double indel, int threads, const uint64_t* a_off, const uint64_t* b_off,
-                      char* anc_all, char* des_all, uint8_t* a_all, uint8_t* b_all);
 
 /* ---- Forward fill + seeded stochastic sampleback ----------------------------------------------
  * coati_gpu_forward   = forward (align_pair.cc:149-152: forward_impl<semiring::log, align_pair_work_t>).

@@ -13,7 +13,7 @@ WORKER = textwrap.dedent("""
     sys.path.insert(0, %r)
     import numpy as np, torch, torch.distributed as dist
     from coati_b200 import dist as cdist
-    from coati_b200.capi import synth_pairs
+    from synth import synth_pairs
     import oracle
     from tests import util
 

@@ -346,7 +346,7 @@ def test_workload_scale_properties(workload, k, tname, n, tables):
     raw-sequence call)."""
     import coati_b200
     from coati_b200 import capi
-    from coati_b200.capi import synth_pairs
+    from synth import synth_pairs
     n = int(os.environ.get("COATI_TEST_PAIRS", n))
     g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
     T = tables[tname]

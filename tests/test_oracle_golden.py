@@ -186,7 +186,7 @@ def test_gtr_q_golden():
 def test_batch_property_checker_on_oracle_output(tables):
     """The vectorised property checker the GPU tests run at workload scale (tests/util.check_batch_properties),
     exercised here on arenas filled by the oracle -- and on deliberately corrupted arenas, which it must reject."""
-    from coati_b200.capi import synth_pairs
+    from synth import synth_pairs
     g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
     for workload, k, tname in ((5, 1, "mg_c5"), (4, 3, "ecm_default")):
         w = synth_pairs(24 if workload == 5 else 6, workload, 42, threads=1)
@@ -227,7 +227,7 @@ def test_entry_point_comparison_on_oracle_output(tables):
     """tests/util.compare_entry_points (used by the GPU workload-scale test) on arenas made by the oracle the
     way the three entry points fill them: scratch bytes after the terminators differ, and the raw-sequence
     call trims and restores end stops (two descendants are made to end in a stop codon)."""
-    from coati_b200.capi import synth_pairs
+    from synth import synth_pairs
     g, e = np.float32(0.001), np.float32(1.0) - np.float32(1.0) / np.float32(6.0)
     T = tables["mg_c5"]
     w = synth_pairs(20, 5, 42, threads=1)

@@ -2,7 +2,7 @@ import os, sys, time
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch, coati_b200
 from coati_b200 import capi
-from coati_b200.capi import synth_pairs
+from synth import synth_pairs
 T = np.load('/root/repo/tests/golden/tables.npz')['mg_c5'].astype(np.float32)
 pinned = []
 def alloc(n):

@@ -5,7 +5,7 @@ if os.environ.get("TRACE", "1") == "1":
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, coati_b200
 from coati_b200 import capi
-from coati_b200.capi import synth_pairs
+from synth import synth_pairs
 T = np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'tables.npz'))['mg_c5'].astype(np.float32)
 pinned = []
 def alloc(n):
