@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.coati_gpu_batch_destroy.restype = None
     # host layer (no GPU): table builder, encoding, seeding, re-scoring
     lib.coati_host_marginal_table.argtypes = [C.c_int, C.c_float, C.c_float, _fp, C.c_int, C.c_int, _fp]
+    lib.coati_host_marginal_table_gtr.argtypes = [C.c_float, C.c_float, _fp, _fp, _fp]
     lib.coati_host_mg94_p.argtypes = [C.c_float, C.c_float, _fp, _fp, _fp]
     lib.coati_host_gtr_q.argtypes = [_fp, _fp, _fp]
     lib.coati_host_encode.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, _u8p, _u8p]
@@ -533,6 +534,18 @@ def host_marginal_table(model="mar-mg", br_len=0.0133, omega=0.2, pi=(0.308, 0.1
     rc = lib.coati_host_marginal_table({"mar-mg": 0, "mar-ecm": 1}[model], br_len, omega, p.ctypes.data_as(_fp),
                                        int(amb == "BEST"), int(msub == "MAX"), out.ctypes.data_as(_fp))
     if rc != 0:
+        raise ValueError("set_subst failed")
+    return out
+
+
+def host_marginal_table_gtr(br_len=0.0133, omega=0.2, pi=(0.308, 0.185, 0.199, 0.308), sigma=(0,) * 6):
+    """mar-mg table with the GTR rates wired through (alignment_t::use_sigma; upstream drops them)."""
+    lib = load_library()
+    out = np.zeros((183, 15), dtype=np.float32)
+    p = np.asarray(pi, dtype=np.float32)
+    sg = np.asarray(sigma, dtype=np.float32)
+    if lib.coati_host_marginal_table_gtr(br_len, omega, p.ctypes.data_as(_fp), sg.ctypes.data_as(_fp),
+                                         out.ctypes.data_as(_fp)) != 0:
         raise ValueError("set_subst failed")
     return out
 

@@ -56,6 +56,9 @@ int main(int argc, char* argv[]) {
                 for(int q = 0; q < 4; ++q) args.aln.pi[q] = std::stof(p.value(o));
             } else if(p.is_flag(o, "-x", "--sigma")) {
                 for(int q = 0; q < 6; ++q) args.aln.sigma[q] = std::stof(p.value(o));
+            } else if(o == "--gtr") {
+                // not an upstream option: let -x/--sigma reach the marginal table (alignment_t::use_sigma)
+                args.aln.use_sigma = true;
             } else if(p.is_flag(o, "-b", "--base-error")) {
                 p.value(o);  // parsed and unused on the marginal path, as upstream
             } else if(p.is_flag(o, "-a", "--ambiguous")) {

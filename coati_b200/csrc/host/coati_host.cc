@@ -1,6 +1,7 @@
-// Host-side C++17 layer of coati-b200 (see coati_host.hpp).  Written from scratch; every function
-// cites the reference lines whose behaviour it keeps.  The DP itself is only ever run through the
-// C ABI (include/coati_gpu.h).
+// Host-side C++17 layer of coati-b200 (see coati_host.hpp): COATi's library surface for the marginal path.
+// Every function cites the reference lines whose BEHAVIOUR it keeps (signatures, exception texts and output
+// bytes are pinned by "drop-in"); the code is this repository's own.  The DP itself is only ever run through
+// the C ABI (include/coati_gpu.h).
 #include "coati_host.hpp"
 
 #include <algorithm>
@@ -9,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 
 #include "../../../include/coati_gpu.h"
@@ -98,80 +100,96 @@ uint8_t get_nuc(uint8_t cod, int pos) {
     return static_cast<uint8_t>((c >> (4 - 2 * pos)) & 3);
 }
 
-// ---- utils.cc:496-528 -------------------------------------------------------------------------------
+// ---- sequence preparation ---------------------------------------------------------------------------
+// One classification of an ancestor codon serves the encoder here and the error reporting of the batch entry
+// points (the device kernel encode_pairs_kernel applies the same rule per codon).
+namespace {
+enum class codon_kind { sense, ambiguous, stop };
+struct codon_code {
+    codon_kind kind;
+    int index61;
+};
+codon_code classify_codon(std::string_view codon) {
+    const int c64 = cod_int(codon);
+    if(c64 < 0) return {codon_kind::ambiguous, -1};
+    if(is_stop(c64)) return {codon_kind::stop, -1};
+    return {codon_kind::sense, cod64_to_61(c64)};
+}
+// a trailing stop codon of `seq` (case-insensitive, U = T), removed from it and returned; "" if there is none
+std::string split_end_stop(std::string& seq) {
+    if(seq.size() < 3) return {};
+    const std::string_view tail(seq.data() + seq.size() - 3, 3);
+    if(!is_stop(cod_int(tail))) return {};
+    std::string stop(tail);
+    seq.resize(seq.size() - 3);
+    return stop;
+}
+}  // namespace
+
+// Behaviour of utils.cc:496-528: ancestor codon -> 3 * cod61 + phase; the first codon that is not a sense codon
+// decides the exception; descendant symbol -> IUPAC code (16 for anything unknown).
 sequence_pair_t marginal_seq_encoding(std::string_view anc, std::string_view des) {
-    sequence_pair_t ret(2);
-    ret[0].reserve(anc.size());
-    ret[1].reserve(des.size());
-    for(size_t i = 0; i < anc.size(); i += 3) {
-        int cod = cod_int(anc.substr(i, 3));
-        if(cod == -1) throw std::invalid_argument("Ambiguous nucleotides in ancestor/reference.");
-        if(is_stop(cod)) throw std::invalid_argument("Early stop codon in ancestor/reference.");
-        cod = cod64_to_61(cod) * 3;
-        ret[0].push_back(static_cast<unsigned char>(cod));
-        ret[0].push_back(static_cast<unsigned char>(cod + 1));
-        ret[0].push_back(static_cast<unsigned char>(cod + 2));
+    sequence_pair_t enc(2);
+    auto& a = enc[0];
+    auto& b = enc[1];
+    a.resize(anc.size() / 3 * 3 + (anc.size() % 3 ? 3 : 0));
+    size_t w = 0;
+    for(size_t pos = 0; pos < anc.size(); pos += 3) {
+        const codon_code cc = classify_codon(anc.substr(pos, 3));
+        switch(cc.kind) {
+        case codon_kind::ambiguous: throw std::invalid_argument("Ambiguous nucleotides in ancestor/reference.");
+        case codon_kind::stop: throw std::invalid_argument("Early stop codon in ancestor/reference.");
+        case codon_kind::sense: break;
+        }
+        for(int phase = 0; phase < 3; ++phase) a[w++] = static_cast<unsigned char>(3 * cc.index61 + phase);
     }
-    for(unsigned char nuc : des) ret[1].push_back(nuc < 128 ? nt16(nuc) : 16);
-    return ret;
+    b.resize(des.size());
+    std::transform(des.begin(), des.end(), b.begin(),
+                   [](char ch) { return static_cast<unsigned char>(ch) < 128 ? nt16(static_cast<unsigned char>(ch)) : 16; });
+    return enc;
 }
 
-// ---- utils.cc:789-803 -------------------------------------------------------------------------------
+// Behaviour of utils.cc:789-803: make the reference sequence the first one.
 void order_ref(alignment_t& aln) {
-    if(aln.data.names[0] == aln.refs) {
-    } else if(aln.data.names[1] == aln.refs || aln.rev) {
-        std::swap(aln.data.names[0], aln.data.names[1]);
-        std::swap(aln.data.seqs[0], aln.data.seqs[1]);
-    } else {
-        throw std::invalid_argument("Name of reference sequence not found.");
-    }
+    auto& names = aln.data.names;
+    const bool first_is_ref = names[0] == aln.refs;
+    const bool second_is_ref = names[1] == aln.refs;
+    if(first_is_ref) return;
+    if(!second_is_ref && !aln.rev) throw std::invalid_argument("Name of reference sequence not found.");
+    std::swap(names[0], names[1]);
+    std::swap(aln.data.seqs[0], aln.data.seqs[1]);
 }
 
-// ---- utils.cc:945-967 -------------------------------------------------------------------------------
+// Behaviour of utils.cc:945-967: strip one terminal stop codon per sequence and remember it.
 void trim_end_stops(data_t& data) {
-    for(size_t i = 0; i < data.size(); ++i) {
-        const std::string& seq = data.seqs[i];
-        const size_t len = seq.size();
-        if(len < 3) {
-            data.stops.emplace_back("");
-            continue;
-        }
-        const std::string last = seq.substr(len - 3);
-        if(is_stop(cod_int(last))) {
-            data.stops.push_back(last);
-            data.seqs[i].erase(len - 3);
-        } else {
-            data.stops.emplace_back("");
-        }
-    }
+    const size_t n = data.size();
+    for(size_t i = 0; i < n; ++i) data.stops.push_back(split_end_stop(data.seqs[i]));
 }
 
-// ---- utils.cc:1044-1063 -----------------------------------------------------------------------------
+// Behaviour of utils.cc:1044-1063: put the stops back; a stop facing no stop is aligned to a gap codon and
+// charged one gap of three nucleotides.
 void restore_end_stops(data_t& data, const gap_t& gap) {
     if(data.stops.size() != 2) throw std::runtime_error("Error restoring end stop codons.");
-    const float_t gap_score = ::logf(gap.open * gap.extend * gap.extend);
-    if(data.stops[0].size() == data.stops[1].size()) {
-        data.seqs[0].append(data.stops[0]);
-        data.seqs[1].append(data.stops[1]);
-    } else if(data.stops[0].empty()) {
-        data.seqs[0].append("---");
-        data.seqs[1].append(data.stops[1]);
-        data.score += gap_score;
-    } else if(data.stops[1].empty()) {
-        data.seqs[0].append(data.stops[0]);
-        data.seqs[1].append("---");
-        data.score += gap_score;
-    }
+    const std::string& s0 = data.stops[0];
+    const std::string& s1 = data.stops[1];
+    const bool lone = s0.size() != s1.size() && (s0.empty() || s1.empty());
+    if(s0.size() != s1.size() && !lone) return;  // (unreachable: a stop is 0 or 3 symbols)
+    data.seqs[0] += lone && s0.empty() ? std::string("---") : s0;
+    data.seqs[1] += lone && s1.empty() ? std::string("---") : s1;
+    if(lone) data.score += ::logf(gap.open * gap.extend * gap.extend);
 }
 
-// ---- utils.cc:809-838 -------------------------------------------------------------------------------
+// Behaviour of utils.cc:809-838: the checks marg_alignment makes before aligning (lengths are tested on the
+// untrimmed sequences), then the stop trimming.
 void process_marginal(alignment_t& aln) {
     if(aln.data.size() != 2) throw std::invalid_argument("Exactly two sequences required.");
-    if(!aln.refs.empty() || aln.rev) order_ref(aln);
-    const size_t len_a = aln.seq(0).length(), len_b = aln.seq(1).length();
-    if(len_a % 3 != 0 || len_a % aln.gap.len != 0)
+    const bool reorder = !aln.refs.empty() || aln.rev;
+    if(reorder) order_ref(aln);
+    const size_t unit = aln.gap.len;
+    const size_t la = aln.seq(0).length(), lb = aln.seq(1).length();
+    if(la % 3 || la % unit)
         throw std::invalid_argument("Length of reference sequence must be multiple of 3 and gap unit length.");
-    if(len_b % aln.gap.len != 0)
+    if(lb % unit)
         throw std::invalid_argument("Length of descendant sequence must be multiple of gap unit length.");
     trim_end_stops(aln.data);
 }
@@ -433,8 +451,13 @@ void set_subst(alignment_t& aln) {
         // NB marginalised with the caller's pi (MG94 default), not ecm_pi -- as upstream (:603-604)
         aln.subst_matrix = marginal_p(ecm_p(aln.br_len, aln.omega), aln.pi, aln.amb, aln.sub);
     } else if(aln.model == "mar-mg") {
-        // sigma never reaches this path upstream (:606): mg94_p is called without it
-        aln.subst_matrix = marginal_p(mg94_p(aln.br_len, aln.omega, aln.pi), aln.pi, aln.amb, aln.sub);
+        // Upstream, -x/--sigma is parsed but never reaches this path: set_subst calls mg94_p without it
+        // (utils.cc:606), so the GTR rates of mutation_coati.cc:317-354 are dead code from the CLI.  Default:
+        // the same (drop-in).  aln.use_sigma (--gtr on the CLI) is the documented deviation SURVEY 8(f)-4 asks
+        // for: the six rates go to mg94_p, which builds the nucleotide matrix with gtr_q when any is positive.
+        const matrix61_t P = aln.use_sigma ? mg94_p(aln.br_len, aln.omega, aln.pi, aln.sigma)
+                                           : mg94_p(aln.br_len, aln.omega, aln.pi);
+        aln.subst_matrix = marginal_p(P, aln.pi, aln.amb, aln.sub);
     } else {
         throw std::invalid_argument("Mutation model unknown.");
     }
@@ -532,35 +555,44 @@ data_t read_fasta(std::istream& in) {  // fasta.cc:39-76
     return fasta;
 }
 
-data_t read_phylip(std::istream& in) {  // phylip.cc:37-97
-    data_t phylip;
+// PHYLIP as COATi reads and writes it: a header "<count> <columns>", then interleaved blocks; the first block
+// carries the names in a 10-character field followed by 50 columns, later blocks 60 columns per row.
+namespace {
+constexpr size_t kPhyName = 10, kPhyFirst = 50, kPhyBlock = 60;
+std::string without_space(std::string_view s) {
+    std::string o;
+    o.reserve(s.size());
+    std::copy_if(s.begin(), s.end(), std::back_inserter(o), [](unsigned char c) { return !std::isspace(c); });
+    return o;
+}
+}  // namespace
+
+// Behaviour of phylip.cc:37-97.
+data_t read_phylip(std::istream& in) {
+    std::string tok_count, tok_width;
+    in >> tok_count >> tok_width;
+    const size_t count = static_cast<size_t>(std::stoi(tok_count));
+    (void)std::stoi(tok_width);  // the declared width is validated as a number and otherwise ignored upstream
+    data_t d;
+    d.names.assign(count, {});
+    d.seqs.assign(count, {});
     std::string line;
-    in >> line;
-    const int n_seqs = std::stoi(line);
-    in >> line;
-    const int len_seqs = std::stoi(line);
-    (void)len_seqs;
-    phylip.names.resize(n_seqs);
-    phylip.seqs.resize(n_seqs);
-    auto strip = [](std::string s) {
-        s.erase(std::remove_if(s.begin(), s.end(), [](unsigned char c) { return std::isspace(c); }), s.end());
-        return s;
-    };
-    for(int i = 0; i < n_seqs; i++) {
+    // named rows: the rest of the header line reads as one empty line, which a row may skip once
+    for(size_t row = 0; row < count; ++row) {
         std::getline(in, line);
         if(line.empty()) std::getline(in, line);
-        phylip.names[i] = strip(line.substr(0, 10));
-        phylip.seqs[i] = line.size() > 10 ? strip(line.substr(10)) : std::string();
+        const std::string_view v(line);
+        d.names[row] = without_space(v.substr(0, kPhyName));
+        d.seqs[row] = v.size() > kPhyName ? without_space(v.substr(kPhyName)) : std::string();
     }
-    size_t count = 0;
-    while(in.good()) {
-        const size_t index = count % n_seqs;
+    // continuation rows go round-robin to the sequences; blank lines separate blocks and carry nothing
+    for(size_t row = 0; in.good();) {
         std::getline(in, line);
         if(line.empty()) continue;
-        phylip.seqs[index] += strip(line);
-        count++;
+        d.seqs[row % count] += without_space(line);
+        ++row;
     }
-    return phylip;
+    return d;
 }
 
 // json.cc:44-79: {"alignment": {name: seq, ...}, "score": x} -- a minimal reader for exactly the
@@ -624,17 +656,19 @@ void write_fasta(const data_t& d, std::ostream& out) {  // fasta.cc:182-191
         for(size_t j = 0; j < d.seqs[i].size(); j += 60) out << d.seqs[i].substr(j, 60) << std::endl;
     }
 }
-void write_phylip(const data_t& d, std::ostream& out) {  // phylip.cc:194-217
-    out << d.size() << " " << d.seqs[0].length() << std::endl;
-    size_t i = 50;
-    for(size_t j = 0; j < d.size(); j++) {
-        std::string name = d.names[j].substr(0, 10);
-        name.append(10 - name.length(), ' ');
-        out << name << d.seqs[j].substr(0, i) << std::endl;
-    }
-    out << std::endl;
-    for(; i < d.seqs[0].length(); i += 60) {
-        for(size_t j = 0; j < d.size(); j++) out << d.seqs[j].substr(i, 60) << std::endl;
+// Behaviour of phylip.cc:194-217 (byte for byte: names cut or padded to 10, a blank line after every block).
+void write_phylip(const data_t& d, std::ostream& out) {
+    const size_t count = d.size(), columns = d.seqs[0].length();
+    out << count << " " << columns << std::endl;
+    for(size_t from = 0, width = kPhyFirst; from == 0 || from < columns; from += width, width = kPhyBlock) {
+        for(size_t row = 0; row < count; ++row) {
+            if(from == 0) {
+                std::string field = d.names[row].substr(0, kPhyName);
+                field.resize(kPhyName, ' ');
+                out << field;
+            }
+            out << d.seqs[row].substr(std::min(from, d.seqs[row].size()), width) << std::endl;
+        }
         out << std::endl;
     }
 }
@@ -905,6 +939,45 @@ int coati_host_marginal_table(int model, float br_len, float omega, const float*
         aln.sub = msub ? coati::MarginalSubst::MAX : coati::MarginalSubst::SUM;
         coati::set_subst(aln);
         std::memcpy(out, aln.subst_matrix.v.data(), 183 * 15 * sizeof(float));
+    } catch(...) {
+        return -1;
+    }
+    return 0;
+}
+
+// the same with the GTR rates wired through (alignment_t::use_sigma), mar-mg only
+int coati_host_marginal_table_gtr(float br_len, float omega, const float* pi, const float* sigma, float* out) {
+    try {
+        coati::alignment_t aln;
+        aln.br_len = br_len;
+        aln.omega = omega;
+        aln.pi.assign(pi, pi + 4);
+        aln.sigma.assign(sigma, sigma + 6);
+        aln.use_sigma = true;
+        coati::set_subst(aln);
+        std::memcpy(out, aln.subst_matrix.v.data(), 183 * 15 * sizeof(float));
+    } catch(...) {
+        return -1;
+    }
+    return 0;
+}
+
+// write_phylip of two rows, read back with read_phylip: returns 0 when names (cut to 10) and rows survive
+int coati_host_phylip_roundtrip(const char* n0, const char* s0, const char* n1, const char* s1, char* text,
+                                size_t cap) {
+    try {
+        coati::data_t d;
+        d.names = {n0, n1};
+        d.seqs = {s0, s1};
+        std::ostringstream os;
+        coati::write_phylip(d, os);
+        const std::string t = os.str();
+        if(t.size() + 1 > cap) return -2;
+        std::memcpy(text, t.c_str(), t.size() + 1);
+        std::istringstream is(t);
+        const coati::data_t r = coati::read_phylip(is);
+        if(r.seqs != d.seqs) return -3;
+        if(r.names[0] != d.names[0].substr(0, 10) || r.names[1] != d.names[1].substr(0, 10)) return -4;
     } catch(...) {
         return -1;
     }

@@ -1,6 +1,6 @@
 // Host-side C++17 layer above the C ABI: COATi's library surface for the marginal path
 // (`coati::alignment_t` in; `marg_alignment` / `marg_sample` / `alignment_score` semantics and
-// FASTA / PHYLIP / JSON out), written from scratch.  The dynamic programs run ONLY through
+// FASTA / PHYLIP / JSON out).  The dynamic programs run ONLY through
 // include/coati_gpu.h -- there is no CPU implementation of the hot path in here.
 //
 // Mirrors (paths relative to the reference):
@@ -66,6 +66,9 @@ struct alignment_t {
     std::string rate;  // --sub: path to a CSV codon rate matrix (io.cc:48-88)
     gap_t gap;
     std::vector<float_t> sigma{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // false (default): sigma is ignored by the marginal models exactly as upstream (utils.cc:606); true: the GTR
+    // rates reach mg94_p (mutation_coati.cc:317-354) -- a deliberate, documented deviation
+    bool use_sigma{false};
     subst_table_t subst_matrix;
     std::string output;
     bool score{false};

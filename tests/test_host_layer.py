@@ -189,3 +189,43 @@ def test_parse_matrix_csv_self_consistency(lib, tmp_path):
         fh.write("AAA,AAA,0\n")
     assert lib.coati_host_parse_matrix_csv(str(path).encode(), P.ctypes.data_as(_fp)) == -2
     assert lib.coati_host_parse_matrix_csv(b"", P.ctypes.data_as(_fp)) == -2
+
+
+def test_gtr_sigma_reaches_the_table_only_when_asked():
+    """upstream parses -x/--sigma and then drops it (utils.cc:606).  Default here: the same table as
+    without sigma (drop-in).  alignment_t::use_sigma (--gtr): the rates go through gtr_q into mg94_p
+    (mutation_coati.cc:317-354); checked against the numpy restatement with scipy's expm (table parity is pinned to
+    the reference's own 1e-5 class of tolerance, not to bits: Eigen is absent)."""
+    from coati_b200 import capi
+    from oracle import table as otable
+    pi = (0.308, 0.185, 0.199, 0.308)
+    sigma = (0.009489730, 0.039164824, 0.004318182, 0.015438693, 0.038734091, 0.008550000)   # mutation_coati.cc:360
+    plain = capi.host_marginal_table("mar-mg", br_len=0.0133, omega=0.2, pi=pi)
+    wired = capi.host_marginal_table_gtr(0.0133, 0.2, pi, sigma)
+    want = otable.marginal_p(otable.mg94_p(0.0133, 0.2, pi, sigma), pi)
+    assert np.allclose(wired, want, rtol=3e-5, atol=3e-6)
+    assert not np.allclose(wired, plain, rtol=1e-3)           # the rates matter
+    zero = capi.host_marginal_table_gtr(0.0133, 0.2, pi, (0,) * 6)
+    assert np.array_equal(zero, plain)                         # all-zero sigma = Yang-94 rates, as mg94_p decides
+
+
+def test_phylip_round_trip_and_layout(tmp_path):
+    """write_phylip / read_phylip (phylip.cc:37-97, 194-217): names cut or padded to 10 characters, 50 columns in
+    the first block, 60 in the following ones, a blank line after every block; the reader gives the rows back."""
+    import ctypes as C
+    import coati_b200
+    lib = coati_b200.load_library()
+    if not hasattr(lib, "coati_host_phylip_roundtrip"):
+        import pytest
+        pytest.skip("hook missing")
+    lib.coati_host_phylip_roundtrip.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    a = "ACGT" * 43 + "A-"          # 174 columns: 50 + 60 + 60 + 4
+    b = "TG-A" * 43 + "CC"
+    out = C.create_string_buffer(4096)
+    assert lib.coati_host_phylip_roundtrip(b"a_very_long_name", a.encode(), b"s2", b.encode(), out, 4096) == 0
+    text = out.value.decode()
+    lines = text.split("\n")
+    assert lines[0] == "2 174"
+    assert lines[1] == "a_very_lon" + a[:50] and lines[2] == "s2        " + b[:50] and lines[3] == ""
+    assert lines[4] == a[50:110] and lines[5] == b[50:110] and lines[6] == ""
+    assert lines[10] == a[170:] and lines[11] == b[170:] and lines[12] == ""
