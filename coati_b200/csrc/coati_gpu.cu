@@ -145,10 +145,15 @@ struct HostPool {
 struct coati_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   // all work of the public staged API
-    // lanes of the pipelined coati_gpu_viterbi_batch: the fills of lane i run on lane_fill[i] (default
-    // priority; lane_fill[0] == stream), everything else of the lane on the high-priority lane_hi[i]
+    // lanes of the pipelined batch calls: everything of a sub-batch but its fills (H2D, encode, traceback,
+    // expand, D2H) runs on the lane's high-priority stream lane_hi[i]; the fills of all lanes alternate between
+    // two low-priority fill streams.  A fill's grid is persistent and takes every CTA slot, so the next fill
+    // (other stream) moves in as the CTAs of the running one retire: the tail of a fill -- a few warps still on
+    // their 2400-nt pairs, 2 ms of a 12 ms fill at 32 k pairs -- is covered, and there are never three fills
+    // competing from the start.  Measured on C5, 1 M pairs cut into 31 sub-batches: one stream per lane (round 1)
+    // 377-490 ms with convoys, one shared stream 410-490 ms (tails exposed), two alternating streams 326 ms.
     static constexpr int NLANE = 3;
-    cudaStream_t lane_fill[NLANE] = {nullptr, nullptr, nullptr};
+    cudaStream_t fill_stream = nullptr, fill_stream2 = nullptr;
     cudaStream_t lane_hi[NLANE] = {nullptr, nullptr, nullptr};
     cudaDeviceProp prop{};
     bool model_set = false;
@@ -315,7 +320,7 @@ double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
 struct coati_gpu_batch {
     coati_gpu_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;  // every operation of this batch is ordered on this stream ...
-    cudaStream_t fill_stream = nullptr;  // ... except the fills, fenced by events when it is another stream
+    cudaStream_t fill_stream = nullptr, fill_stream2 = nullptr;  // ... except the fills, fenced by events when it is another stream
     size_t npairs = 0;
     uint64_t a_total = 0, b_total = 0, out_total = 0;
     std::vector<PairDesc> descs;  // sorted (largest lattice first)
@@ -389,12 +394,10 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     {
         int least = 0, greatest = 0;
         bool ok = cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
-        ctx->lane_fill[0] = ctx->stream;
-        for(int i = 0; ok && i < coati_gpu_ctx::NLANE; ++i) {
-            if(i > 0)
-                ok = cudaStreamCreateWithPriority(&ctx->lane_fill[i], cudaStreamNonBlocking, least) == cudaSuccess;
-            ok = ok && cudaStreamCreateWithPriority(&ctx->lane_hi[i], cudaStreamNonBlocking, greatest) == cudaSuccess;
-        }
+        ok = ok && cudaStreamCreateWithPriority(&ctx->fill_stream, cudaStreamNonBlocking, least) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&ctx->fill_stream2, cudaStreamNonBlocking, least) == cudaSuccess;
+        for(int i = 0; ok && i < coati_gpu_ctx::NLANE; ++i)
+            ok = cudaStreamCreateWithPriority(&ctx->lane_hi[i], cudaStreamNonBlocking, greatest) == cudaSuccess;
         if(!ok) {
             cudaGetLastError();
             coati_gpu_shutdown(ctx);
@@ -445,7 +448,7 @@ extern "C" void coati_gpu_shutdown(coati_gpu_ctx* ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     for(int i = 0; i < coati_gpu_ctx::NLANE; ++i) {
-        cudaStream_t both[2] = {ctx->lane_hi[i], i > 0 ? ctx->lane_fill[i] : nullptr};
+        cudaStream_t both[2] = {ctx->lane_hi[i], i == 0 ? ctx->fill_stream : i == 1 ? ctx->fill_stream2 : nullptr};
         for(cudaStream_t st : both)
             if(st) {
                 cudaStreamSynchronize(st);
@@ -1338,7 +1341,7 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
             raw = rawbuf.data();
         }
         rc = batch_create_on(ctx, pipelined ? ctx->lane_hi[slot] : ctx->stream,
-                             pipelined ? ctx->lane_fill[slot] : ctx->stream, lane_budget, p1 - p0,
+                             pipelined ? ((j & 1) ? ctx->fill_stream2 : ctx->fill_stream) : ctx->stream, lane_budget, p1 - p0,
                              a_off + p0, b_off + p0, &bt[slot], raw, A.model ? A.model + p0 : nullptr);
         if(rc != COATI_GPU_OK) break;
         mark("plan end", p0);
