@@ -205,7 +205,8 @@ class Arena:
             self.off[name] = (total, nbytes)
             total += (nbytes + 4095) & ~4095
         self.total = max(total, 4096)
-        if world == 1:
+        self.shared = world > 1 or os.environ.get("COATI_BENCH_SHM") == "1"   # (the env: A/B of the arena kind at N = 1)
+        if not self.shared:
             from coati_b200.capi import PinnedArena
             self.block = PinnedArena(self.total)
             self.buf = self.block.array
@@ -216,7 +217,8 @@ class Arena:
                 name[0] = "/dev/shm/coati_bench_%s" % uuid.uuid4().hex
                 with open(name[0], "wb") as f:
                     f.truncate(self.total)
-            dist.broadcast_object_list(name, src=0)
+            if dist is not None:
+                dist.broadcast_object_list(name, src=0)
             self.path = name[0]
             self.buf = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.total,))
             self.pinned = lib.coati_gpu_host_register(C.c_void_p(self.buf.ctypes.data), self.total) == 0
@@ -226,14 +228,15 @@ class Arena:
         return self.buf[o:o + n].view(dtype)
 
     def close(self, dist):
-        if self.world == 1:
+        if not self.shared:
             self.buf = None
             self.block.free()
             return
         import ctypes as C
         if self.pinned:
             self.lib.coati_gpu_host_unregister(C.c_void_p(self.buf.ctypes.data))
-        dist.barrier()
+        if dist is not None:
+            dist.barrier()
         if self.rank == 0:
             os.unlink(self.path)
 
@@ -424,6 +427,7 @@ def main():
     for _ in range(e2e_steps):
         e2e_once()
     torch.cuda.synchronize()
+    e2e_own_s = time.perf_counter() - t0       # this rank alone; the reported time also waits for the slowest rank
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -441,17 +445,19 @@ def main():
         c = torch.tensor([float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         launches_all, h2d_all, d2h_all = c.tolist()
-        per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
-        per_rank[rank] = my_cells
+        per_rank = torch.zeros(2, world, dtype=torch.float64, device="cuda")
+        per_rank[0, rank] = my_cells
+        per_rank[1, rank] = 1e3 * e2e_own_s / e2e_steps
         dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
-        shard_cells = per_rank.tolist()
+        shard_cells, e2e_rank_ms = per_rank[0].tolist(), per_rank[1].tolist()
     else:
         launches_all, h2d_all, d2h_all, shard_cells = float(launches), float(h2d), float(d2h), [my_cells]
+        e2e_rank_ms = [1e3 * e2e_own_s / e2e_steps]
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
         extra = run_extras(ctx, capi, w, npairs, cells_total, outs, e2e_steps)
-    arena_pinned = arena.pinned
+    arena_pinned, arena_shared = arena.pinned, arena.shared
     del w, outs, out_a, out_b, out_len, score, status
     arena.close(dist)
     if rank != 0:
@@ -496,14 +502,15 @@ def main():
                    "shard_cells_max_over_mean": max(shard_cells) / (sum(shard_cells) / world),
                    "decision_stream_bytes_rank0": stats["dir_bytes"], "dir_chunks_rank0": stats["chunks"],
                    "gen_seconds": gen_s,
-                   "host_arena": "cudaHostAlloc" if world == 1 else "/dev/shm + cudaHostRegister",
+                   "host_arena": "/dev/shm + cudaHostRegister" if arena_shared else "cudaHostAlloc",
                    "host_arena_pinned": bool(arena_pinned),
                    "collective": None if dist is None else ("NCCL send/recv gather of rows + result records to rank 0, "
                                                             "double-buffered staging copy, side stream"),
                    "nccl_gather_bytes_to_root_per_step": gather_bytes},
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "pairs_per_s": npairs * e2e_steps / e2e_s,
-                "steps": e2e_steps, "api": "coati_gpu_alignpair_batch_ranges, rows delivered to one host arena"},
+                "steps": e2e_steps, "ms_per_step_by_rank": [round(x, 2) for x in e2e_rank_ms],
+                "api": "coati_gpu_alignpair_batch_ranges, rows delivered to one host arena"},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": {"bound": "fp32_issue", "kernel": wl["kernel"], "achieved": ach_tflops,

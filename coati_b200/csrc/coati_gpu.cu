@@ -593,6 +593,8 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
     bt->b_total = npairs ? b_off[npairs] - b0 : 0;
     bt->out_total = bt->a_total + bt->b_total + npairs;
     trace_mark("  plan: host alloc", npairs);
+    uint32_t memo[64][2];
+    for(auto& m : memo) m[0] = 0, m[1] = 0;  // la == 0 never looks itself up
     for(size_t p = 0; p < npairs; ++p) {
         PairDesc& d = bt->descs[p];
         uint64_t la = a_off[p + 1] - a_off[p], lb = b_off[p + 1] - b_off[p];
@@ -612,14 +614,23 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
         d.orig = static_cast<uint32_t>(p);
         d.cfg = 0;
         if(!ctx->force_generic && la > 0 && lb > 0) {
-            double best = 0;
-            for(const PipeCfg& pc : g_pipe_cfgs) {
-                if(pc.k != k || pc.wave || !cfg_eligible(pc, ctx->pipe_scalar) ||
-                   (ctx->force_r && pc.R != ctx->force_r))
-                    continue;
-                const double c = pipe_cost(d.la, d.lb, pc.R);
-                if(d.cfg == 0 || c < best) best = c, d.cfg = pc.R;
+            // rows per lane: the cost model's column factor is the same for every candidate, so the choice
+            // depends on la alone; batches repeat lengths (bins), so remember the last few answers
+            uint32_t& memo_la = memo[(d.la * 2654435761u) >> 26][0];
+            uint32_t& memo_r = memo[(d.la * 2654435761u) >> 26][1];
+            if(memo_la != d.la) {
+                double best = 0;
+                uint32_t r = 0;
+                for(const PipeCfg& pc : g_pipe_cfgs) {
+                    if(pc.k != k || pc.wave || !cfg_eligible(pc, ctx->pipe_scalar) ||
+                       (ctx->force_r && pc.R != ctx->force_r))
+                        continue;
+                    const double c = pipe_cost(d.la, 1000, pc.R);
+                    if(r == 0 || c < best) best = c, r = pc.R;
+                }
+                memo_la = d.la, memo_r = r;
             }
+            d.cfg = memo_r;
             // long pairs (or pairs of a batch too small to fill the GPU) run as an intra-pair wavefront
             const uint64_t cells = la * lb;
             const bool small_batch = npairs < 2048;
@@ -1144,7 +1155,12 @@ static void scan_raw_pairs(uint32_t k, const char* anc_all, const uint64_t* anc_
         const int cod = (n0 << 4) | (n1 << 2) | n2;
         return cod == 48 || cod == 50 || cod == 56;
     };
+    constexpr size_t AHEAD = 16;  // the tails sit hundreds of bytes apart: fetch them ahead of the test
     for(size_t p = p0; p < p1; ++p) {
+        if(p + AHEAD < p1) {
+            __builtin_prefetch(anc_all + anc_off[p + AHEAD + 1] - 3);
+            __builtin_prefetch(des_all + des_off[p + AHEAD + 1] - 3);
+        }
         const uint64_t la = anc_off[p + 1] - anc_off[p], lb = des_off[p + 1] - des_off[p];
         uint8_t f = 0;
         if(la % 3 != 0 || la % k != 0 || lb % k != 0) f |= 0x80;
@@ -1203,15 +1219,23 @@ static double range_cells(const uint64_t* a_off, const uint64_t* b_off, size_t p
     return c;
 }
 
-// Cut [0, npairs) into contiguous chunks of equal WEIGHT (sum of La * Lb): about npairs / chunk of them, rounded
-// up to a multiple of `multiple` so that they divide evenly over that many workers, and none with more than four
-// times `chunk` pairs (a batch sorted by length would otherwise put millions of short pairs into one chunk).
-// Returned heaviest first.
-static void plan_chunks(size_t npairs, const uint64_t* a_off, const uint64_t* b_off, size_t chunk, size_t multiple,
+// Cut [0, npairs) into contiguous chunks of equal WEIGHT (sum of La * Lb), returned heaviest first.
+// How heavy: a fill cannot end before its longest pair does -- one warp sweeps a 2400 x 2400 lattice in about
+// 12 ms while it shares its scheduler with three others -- so a chunk should hold at least that much work for
+// the whole GPU (1.3e10 cells at ~1.06 TCUPS), or its fill ends in a tail of a few busy warps; and about four
+// chunks per worker keep the pipeline of H2D / kernels / D2H and the balance between workers.  The count is
+// rounded up to a multiple of `workers`, and no chunk gets more than 2^17 pairs (a batch sorted by length
+// would otherwise put millions of short pairs into one chunk).
+constexpr double CHUNK_MIN_CELLS = 1.3e10, CHUNK_MAX_CELLS = 2.6e10;
+constexpr size_t CHUNK_MAX_PAIRS = size_t(1) << 17;
+static void plan_chunks(size_t npairs, const uint64_t* a_off, const uint64_t* b_off, size_t workers,
                         std::vector<std::pair<size_t, size_t>>& out, std::vector<double>& cost) {
-    size_t n = std::max<size_t>(1, (npairs + chunk - 1) / chunk);
-    if(multiple > 1 && n > 1) n = std::min(std::max<size_t>(npairs, 1), (n + multiple - 1) / multiple * multiple);
+    workers = std::max<size_t>(1, workers);
     const double total = range_cells(a_off, b_off, 0, npairs);
+    const double target = std::min(CHUNK_MAX_CELLS, std::max(CHUNK_MIN_CELLS, total / (4.0 * (double)workers)));
+    size_t n = std::max<size_t>(1, (size_t)std::llround(total / target));
+    if(n > 1 || workers > 1) n = (n + workers - 1) / workers * workers;
+    n = std::min(n, std::max<size_t>(npairs, 1));
     std::vector<std::pair<size_t, size_t>> r;
     std::vector<double> c;
     size_t p0 = 0;
@@ -1220,7 +1244,7 @@ static void plan_chunks(size_t npairs, const uint64_t* a_off, const uint64_t* b_
         acc += (double)(a_off[p + 1] - a_off[p]) * (double)(b_off[p + 1] - b_off[p]);
         // the k-th cut sits where the running weight passes k / n of the total
         const bool heavy = done + acc >= total * (double)(r.size() + 1) / (double)n;
-        if(p + 1 == npairs || ((heavy || p + 1 - p0 >= 4 * chunk) && npairs - (p + 1) >= 1)) {
+        if(p + 1 == npairs || heavy || p + 1 - p0 >= CHUNK_MAX_PAIRS) {
             r.emplace_back(p0, p + 1);
             c.push_back(acc);
             done += acc, acc = 0, p0 = p + 1;
@@ -1245,9 +1269,12 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
     // Large batches are cut into sub-batches that rotate over the lanes of the context, so that the
     // host-side planning, the H2D copy and the D2H copy of one sub-batch overlap the kernels of its
     // neighbours.
-    const size_t kMinPipe = 32768;
     size_t nsub = 1;
-    if(npairs >= 2 * kMinPipe) nsub = std::min<size_t>(16, npairs / kMinPipe);
+    if(npairs >= 65536) {  // same weight rule as plan_chunks, in input order
+        const double total = range_cells(a_off, b_off, 0, npairs);
+        nsub = (size_t)std::llround(total / std::min(CHUNK_MAX_CELLS, std::max(CHUNK_MIN_CELLS, total / 4.0)));
+        nsub = std::min<size_t>(std::max<size_t>(nsub, 1), npairs / 8192);
+    }
     if(const char* env = std::getenv("COATI_GPU_NSUB")) nsub = std::max(1, std::atoi(env));  // tuning
     if(ctx->dir_budget != 0) nsub = 1;  // an explicit direction budget (tests) keeps the simple path
     const BatchArgs A{npairs, a_all, a_off, b_all, b_off, anc_all, des_all, out_a, out_b, out_len, score, status,
@@ -1293,6 +1320,13 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
         lane_budget = free_b > NSLOT * fixed_sub
                           ? static_cast<uint64_t>((free_b - NSLOT * fixed_sub) * 0.85 / NSLOT) : (1ull << 20);
     }
+    if(pipelined) {
+        // one pinned landing zone per slot, each big enough for the biggest range: taken and given back here so
+        // that no sub-batch has to allocate pinned memory (cudaMallocHost waits for running kernels) mid-pipeline
+        void* zone[NSLOT];
+        for(void*& z : zone) z = ctx->hpool.take((q.max_pairs + 1) * sizeof(PairResult));
+        for(void* z : zone) ctx->hpool.give(z);
+    }
     const bool trace = trace_on();
     auto mark = [&](const char* what, size_t j) { trace_mark(what, j); };
     auto finish = [&](int slot) -> int {
@@ -1323,7 +1357,20 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
     };
     int rc = COATI_GPU_OK;
     size_t p0 = 0, p1 = 0;
-    for(size_t j = 0; rc == COATI_GPU_OK && q.pop(p0, p1); ++j) {
+    // The first range of a call is split: a small head is planned and on the GPU within a millisecond, and the
+    // planning of the rest runs beside its fill.
+    constexpr size_t HEAD_PAIRS = 8192;
+    size_t rest0 = 0, rest1 = 0;
+    auto next_range = [&](size_t j) {
+        if(rest1 > rest0) {
+            p0 = rest0, p1 = rest1, rest1 = rest0;
+            return true;
+        }
+        if(!q.pop(p0, p1)) return false;
+        if(j == 0 && pipelined && p1 - p0 > 2 * HEAD_PAIRS) rest0 = p0 + HEAD_PAIRS, rest1 = p1, p1 = rest0;
+        return true;
+    };
+    for(size_t j = 0; rc == COATI_GPU_OK && next_range(j); ++j) {
         const int slot = (int)(j % NSLOT);
         rc = finish(slot);
         if(rc != COATI_GPU_OK) break;
@@ -1405,12 +1452,6 @@ extern "C" int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, cons
 // runs the three-lane pipeline of the single-device call on whatever chunk it pops next; inside a chunk the
 // planner bins the pairs by kernel configuration and lattice size as always.  Results land in the caller's
 // arenas in input order -- no collective, no second copy.
-static size_t multi_chunk_pairs(size_t npairs, size_t n_workers) {
-    // about eight chunks per device keep the tail short; 8192 pairs still fill a B200 for a fill launch
-    const size_t want = npairs / std::max<size_t>(1, 8 * n_workers);
-    return std::min<size_t>(32768, std::max<size_t>(8192, want));
-}
-
 extern "C" int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n_ctx, size_t npairs,
                                                const char* anc_all, const uint64_t* anc_off,
                                                const char* des_all, const uint64_t* des_off, char* out_a,
@@ -1423,7 +1464,7 @@ extern "C" int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n
         for(int j = 0; j < i; ++j)
             if(ctxs[j] == ctxs[i]) return COATI_GPU_E_ARG;
     }
-    if(n_ctx == 1 || npairs < 2 * 8192)
+    if(n_ctx == 1 || npairs < 4096)
         return coati_gpu_alignpair_batch(ctxs[0], npairs, anc_all, anc_off, des_all, des_off, out_a, out_b, out_len,
                                          score, status);
     const BatchArgs A{npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b, out_len, score,
@@ -1432,7 +1473,7 @@ extern "C" int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n
     try {
         std::vector<std::pair<size_t, size_t>> chunks;
         std::vector<double> cost;
-        plan_chunks(npairs, anc_off, des_off, multi_chunk_pairs(npairs, (size_t)n_ctx), (size_t)n_ctx, chunks, cost);
+        plan_chunks(npairs, anc_off, des_off, (size_t)n_ctx, chunks, cost);
         for(const auto& c : chunks) q.add(c.first, c.second, anc_off, des_off);
     } catch(const std::bad_alloc&) {
         return COATI_GPU_E_NOMEM;
@@ -1458,7 +1499,7 @@ extern "C" size_t coati_gpu_plan_shards(size_t npairs, const uint64_t* a_off, co
     if(!a_off || !b_off || n_shards == 0 || !range_first || !range_last || !range_shard) return 0;
     std::vector<std::pair<size_t, size_t>> chunks;
     std::vector<double> cost;
-    plan_chunks(npairs, a_off, b_off, multi_chunk_pairs(npairs, n_shards), n_shards, chunks, cost);
+    plan_chunks(npairs, a_off, b_off, n_shards, chunks, cost);
     if(chunks.size() > max_ranges) return 0;
     std::vector<double> load(n_shards, 0.0);
     for(size_t j = 0; j < chunks.size(); ++j) {

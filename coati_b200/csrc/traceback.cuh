@@ -308,7 +308,7 @@ traceback_burst_kernel(const PairDesc* __restrict__ pairs, uint32_t p, const uin
 
 // The longest pairs of a batch (listed by the host): run-at-a-time walks, one warp per pair, so the
 // launch that walks the rest one thread per pair is not left waiting for a few thousand-column chains.
-constexpr uint32_t BURST_MIN_COLUMNS = 3000;  // la + lb from which a batch pair is walked by a warp
+constexpr uint32_t BURST_MIN_COLUMNS = 1500;  // la + lb from which a batch pair is walked by a warp
 __host__ __device__ inline bool burst_in_batch(const PairDesc& pd, uint32_t k) {
     return k == 1 && (pd.cfg & 0xffu) != 0 && !(pd.cfg & CFG_WAVE) && pd.la > 0 && pd.lb > 0 &&
            pd.la + pd.lb >= BURST_MIN_COLUMNS;

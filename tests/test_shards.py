@@ -32,14 +32,17 @@ def test_plan_covers_balances_and_is_deterministic(npairs, shards):
     csum = np.concatenate(([0.0], np.cumsum(cells)))
     cost = csum[last.astype(np.int64)] - csum[first.astype(np.int64)]
     assert np.all(np.diff(cost) <= 1e-6 * cost.max())
-    assert (last - first).max() <= 4 * 32768
+    assert (last - first).max() <= 1 << 17
+    # chunks are sized by weight: at least a fill's worth of work each unless the batch is too small for that
+    if len(first) > shards:
+        assert cost.min() > 0.5 * 1.3e10
     # greedy LPT: no shard exceeds the mean by more than one chunk; on the bench workload within 4 %
     load = np.bincount(shard, weights=cost, minlength=shards)
     used = min(shards, len(first))
     assert load.max() <= load.sum() / used + cost.max() + 1e-6
     if npairs >= 100_000:
         assert load.max() / (load.sum() / shards) < 1.04
-        assert 3 * shards <= len(first) <= npairs // 8192 + shards + 1
+        assert shards <= len(first) <= npairs // 8192 + shards + 1
 
 
 def test_plan_orders_a_sorted_batch_by_weight():
