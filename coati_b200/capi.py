@@ -23,6 +23,8 @@ class CoatiGpuError(RuntimeError):
 
 
 def library_path() -> str:
+    if os.environ.get("COATI_GPU_LIB"):   # A/B builds of the same library (tools/gpu experiments)
+        return os.environ["COATI_GPU_LIB"]
     return os.path.join(_HERE, "libcoati_gpu.so")
 
 

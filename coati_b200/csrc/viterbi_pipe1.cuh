@@ -106,7 +106,28 @@ __device__ __forceinline__ void st_boundary(float2* p, float x, float y) {
     if(WAVE) asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
     else *p = make_float2(x, y);
 }
-constexpr uint32_t WAVE_BLOCK = 32;  // columns of the row above fetched per refill (one per lane)
+// The row above arrives from another SM through L2 (~700 cycles), so it is fetched WAVE_G columns at a time
+// (lane j % WAVE_G holds column base + j), one granule ahead of use and WITHOUT waiting: the load is issued
+// when the previous granule becomes current and only examined when its own turn comes (re-polled then if the
+// producer had not got there).  Round 1 fetched whole 32-column blocks and waited for them a block ahead.
+// Measured on B200 (tools/gpu/run16.sh: granule 8 / 16 / 32, sleep 0 / 20 / 40 ns between polls; fill ms at
+// 10k / 40k / 160k): R = 4: 2.36-2.49 / 9.8-10.3 / 55-58 against 2.81 / 11.5 / 68.7 before; R = 10: 3.0-3.1 /
+// 12.3-12.5 / 49.6-50.6 against 2.92 / 11.75 / 47.2.  The granule hardly matters; 16 with a 20 ns sleep is kept.
+#ifndef COATI_WAVE_G
+#define COATI_WAVE_G 16
+#endif
+#ifndef COATI_WAVE_SLEEP
+#define COATI_WAVE_SLEEP 20
+#endif
+constexpr uint32_t WAVE_G = COATI_WAVE_G;
+// A symbol of the descendant, loaded NOW into a register that is then kept: with a plain `b[i]` the compiler
+// re-loads the byte at the point of use instead (the pointer is const __restrict__), which put an L2 round trip
+// on every granule swap of the wavefront (14 % of its time in the first profile of this scheme).
+__device__ __forceinline__ uint32_t ld_symbol_now(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 // NC = substitution-table columns kept per lane: 16 (all IUPAC codes) or 4 when no descendant of the
 // batch carries an ambiguity code (the common case) -- a quarter of the shared memory, so more
@@ -174,13 +195,14 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         for(uint32_t band = band0; band < (WAVE ? band0 + 1 : nbands); ++band) {
             const float2* bin = bnd + (size_t)(WAVE ? band : (band & 1)) * 2 * bnd_stride;
             float2* bout = bnd + (size_t)(WAVE ? band + 1 : ((band + 1) & 1)) * 2 * bnd_stride;
-            // WAVE: one column of the row above per lane, polled until the producer's value is there
-            auto load_block = [&](uint32_t col0) {
-                const float2* src = bin + min(col0 + (uint32_t)lane, lb);
-                float2 v = ld_relaxed_f2(src);
-                while(__any_sync(FULL, v.x != v.x)) {  // NaN sentinel: not written yet
-                    __nanosleep(40);
-                    v = ld_relaxed_f2(src);
+            // WAVE: WAVE_G columns of the row above, one per lane (mod WAVE_G); peek issues the load, settle
+            // re-polls until the producer's values are there (NaN sentinel: not written yet)
+            const uint32_t gl = (uint32_t)lane & (WAVE_G - 1);
+            auto peek = [&](uint32_t col0) { return ld_relaxed_f2(bin + min(col0 + gl, lb)); };
+            auto settle = [&](float2 v, uint32_t col0) {
+                while(__any_sync(FULL, v.x != v.x)) {
+                    if(COATI_WAVE_SLEEP) __nanosleep(COATI_WAVE_SLEEP);
+                    v = peek(col0);
                 }
                 return v;
             };
@@ -221,11 +243,11 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             float2 blkA = make_float2(0.f, 0.f), blkB = blkA;
             uint32_t symA = 0, symB = 0;
             if(WAVE) {
-                const float2 first = load_block(1u - (uint32_t)lane);  // every lane: column 1
-                blkA = load_block(2u);
-                symA = b[min(1u + lane, lb - 1)];
-                blkB = load_block(2u + WAVE_BLOCK);
-                symB = b[min(1u + WAVE_BLOCK + lane, lb - 1)];
+                const float2 first = settle(peek(1u - gl), 1u - gl);  // every lane: column 1
+                blkA = settle(peek(2u), 2u);
+                symA = ld_symbol_now(b + min(1u + gl, lb - 1));
+                blkB = peek(2u + WAVE_G);
+                symB = ld_symbol_now(b + min(1u + WAVE_G + gl, lb - 1));
                 if(lane == 31) outX = first.x, outY = first.y, boff = (uint32_t)b[0] * 512u;
             } else if(lane == 31) {
                 const float2 v = bin[1];
@@ -238,24 +260,23 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             // blocks of 32 steps = one word of every decision plane; the flush sits between blocks
             for(uint32_t t0 = 0; t0 < nsteps; t0 += 32) {
               const uint32_t t1 = min(t0 + 32u, nsteps);
-              if(WAVE && t0 != 0) {  // block t0 / 32 becomes current; refill the next
-                  static_assert(WAVE_BLOCK == 32, "refill once per flush block");
-                  blkA = blkB, symA = symB;
-                  blkB = load_block(t0 + WAVE_BLOCK + 2);
-                  symB = b[min(t0 + WAVE_BLOCK + 1 + lane, lb - 1)];
-              }
               const float2* pbin = bin + t0 + 2;  // lane 0's inputs for the NEXT step (column t + 2);
               const uint8_t* pb = b + t0 + 1;     // both arrays are padded past column lb
               for(uint32_t t = t0; t < t1; ++t, ++u) {
+                if(WAVE && (t & (WAVE_G - 1)) == 0 && t != 0) {  // the next granule becomes current
+                    blkA = settle(blkB, t + 2), symA = symB;
+                    blkB = peek(t + WAVE_G + 2);
+                    symB = ld_symbol_now(b + min(t + WAVE_G + 1 + gl, lb - 1));
+                }
                 const float recvX = __shfl_sync(FULL, outX, rot);
                 const float recvY = __shfl_sync(FULL, outY, rot);
                 const uint32_t bo = __shfl_sync(FULL, boff, rot);
                 float2 bnv;
                 uint32_t bl;
                 if(WAVE) {
-                    bnv.x = __shfl_sync(FULL, blkA.x, t - t0);
-                    bnv.y = __shfl_sync(FULL, blkA.y, t - t0);
-                    bl = __shfl_sync(FULL, symA, t - t0);
+                    bnv.x = __shfl_sync(FULL, blkA.x, t & (WAVE_G - 1));
+                    bnv.y = __shfl_sync(FULL, blkA.y, t & (WAVE_G - 1));
+                    bl = __shfl_sync(FULL, symA, t & (WAVE_G - 1));
                 } else {  // uniform addresses, written by this warp one band earlier
                     bnv = *pbin++;
                     bl = *pb++;
