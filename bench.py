@@ -146,19 +146,19 @@ def emit(line):
 # ---------------------------------------------------------------------------------------------------
 # CPU legs: the reference's own viterbi_mem + traceback_viterbi (oracle/_ref, else the C port), ONE PROCESS PER
 # CORE, each on its own contiguous block of the same seeded pair stream.
-def cpu_reference_run(wl, npairs_total, seconds, procs, table, first=0):
+def cpu_reference_run(wl, npairs_total, seconds, procs, table, first=0, lib=None, flags="-O3 -DNDEBUG"):
     from tools import cpu_worker
     est_gcups_core = 0.05
     cells_per_pair = 338_000 if wl["id"] == 5 else 2_900_000
     n = int(max(procs, min(npairs_total, seconds * est_gcups_core * 1e9 * procs / cells_per_pair)))
-    res = cpu_worker.run_pool(wl["id"], wl["seed"], first, n, table, float(G_OPEN), float(G_EXT), wl["k"], procs)
+    res = cpu_worker.run_pool(wl["id"], wl["seed"], first, n, table, float(G_OPEN), float(G_EXT), wl["k"], procs, lib)
     cells = sum(r["cells"] for r in res)
     secs = max(r["seconds"] for r in res)         # all workers start together: the slowest one is the wall time
     kind = res[0]["kind"]
     return dict(value=cells / secs / 1e9, unit="GCUPS", cores=procs, kind=kind, seconds=secs, pairs=n,
                 pairs_per_s=n / secs, cells=cells,
                 sample=f"first {n} pairs of the seeded {wl['desc'].split(':')[0]} stream (i.i.d. length bins, "
-                       f"{cells:.3g} cells), viterbi_mem+traceback_viterbi, {procs} processes x 1 thread, -O3 -DNDEBUG")
+                       f"{cells:.3g} cells), viterbi_mem+traceback_viterbi, {procs} processes x 1 thread, {flags}")
 
 
 def run_reference(args, wl, table):
@@ -533,6 +533,15 @@ def main():
                 if k in ("value", "unit", "cores", "kind", "sample", "pairs_per_s")}
         except Exception as ex:  # the checker failing must not hide the measurement
             line["cpu_baseline"] = {"error": repr(ex)}
+        o2g = os.path.join(ROOT, "oracle", "_ref", "libcoati_ref_o2g.so")
+        if os.path.exists(o2g) and not args.no_extra:
+            try:  # once: the reference as its DEFAULT Meson build compiles it
+                r = cpu_reference_run(wl, npairs, min(4.0, args.cpu_seconds), os.cpu_count() or 1, want, lib=o2g,
+                                      flags="-O2 -g, assertions on (Meson default buildtype=debugoptimized)")
+                line.setdefault("extra", {})["cpu_baseline_meson_default_build"] = {
+                    k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as ex:
+                line.setdefault("extra", {})["cpu_baseline_meson_default_build"] = {"error": repr(ex)}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -159,14 +159,15 @@ def collect(ctx, which=("c1", "c2", "c3", "c4", "fwd"), max_ref_len=10500):
                                                                           "equal to the oracle (rows, score bits)"}
         del w, oa, ob
     if "fwd" in which:
-        # batched Forward: one warp per pair; 512 copies of the C2 pair (177 k cells each, 12 B/cell stored)
+        # batched Forward: one warp per pair; 4096 copies of the C2 pair (177 k cells each, 12 B/cell stored = 8.7 GB):
+        # enough pairs for four resident warps per scheduler
         (_, anc), (_, des) = util.load_fasta("example-003")
         anc, _ = oracle.trim_end_stop(anc)
         des, _ = oracle.trim_end_stop(des)
         a, b = oracle.encode_pair(anc, des)
         T = tables["mg_golden"]
         ctx.set_model(T, g, e, 1)
-        npairs = 512
+        npairs = 4096
         pk = PackedPairs([a] * npairs, [b] * npairs, [anc] * npairs, [des] * npairs)
         fb = ctx.forward_batch(pk)
         fb.free()
@@ -176,7 +177,7 @@ def collect(ctx, which=("c1", "c2", "c3", "c4", "fwd"), max_ref_len=10500):
         t_cpu, mats = wall(lambda: oracle.fill(1, a, b, T), reps=1)
         ok = all(_bits(term[p][x]) == _bits(mats[x][-1, -1]) for p in (0, npairs - 1) for x in range(3))
         cells = npairs * len(a) * len(b)
-        out["forward_batch_512x_example-003"] = {
+        out["forward_batch_4096x_example-003"] = {
             "pairs": npairs, "cells": cells, "kernel_ms": ms, "gcups": cells / (ms / 1e3) / 1e9,
             "cpu_baseline": {"kind": "port", "cores": 1, "ms_per_pair": 1e3 * t_cpu,
                              "gcups": len(a) * len(b) / t_cpu / 1e9}, "parity": bool(ok),
