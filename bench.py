@@ -283,6 +283,10 @@ def main():
     from synth import synth_offsets, synth_pairs
 
     rank, world, local = dist_env()
+    if os.environ.get("COATI_TRACE_DIR"):   # diagnostics: every rank's stderr (COATI_GPU_TRACE timeline) to its own file
+        os.makedirs(os.environ["COATI_TRACE_DIR"], exist_ok=True)
+        fd = os.open(os.path.join(os.environ["COATI_TRACE_DIR"], "rank%d.log" % rank), os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        os.dup2(fd, 2)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:

@@ -491,9 +491,11 @@ def alignpair_batch_ranges(ctx: "Context", w, outs, first, last):
     out_a, out_b, out_len, score, status = outs
     first = np.ascontiguousarray(first, dtype=np.uint64)
     last = np.ascontiguousarray(last, dtype=np.uint64)
+    rows = os.environ.get("COATI_DIAG_NO_ROWS") != "1"   # diagnostics: skip the D2H of the rows
     ctx._check(ctx.lib.coati_gpu_alignpair_batch_ranges(
         ctx.h, len(w["a_off"]) - 1, _vp(w["anc_all"]), w["a_off"].ctypes.data_as(_u64p), _vp(w["des_all"]),
-        w["b_off"].ctypes.data_as(_u64p), _vp(out_a), _vp(out_b), out_len.ctypes.data_as(_u64p),
+        w["b_off"].ctypes.data_as(_u64p), _vp(out_a) if rows else None, _vp(out_b) if rows else None,
+        out_len.ctypes.data_as(_u64p),
         score.ctypes.data_as(_fp), status.ctypes.data_as(_i32p), len(first), first.ctypes.data_as(_u64p),
         last.ctypes.data_as(_u64p)))
 

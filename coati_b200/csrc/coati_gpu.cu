@@ -1224,7 +1224,7 @@ static double range_cells(const uint64_t* a_off, const uint64_t* b_off, size_t p
 // 12 ms while it shares its scheduler with three others -- so a chunk should hold at least that much work for
 // the whole GPU (1.3e10 cells at ~1.06 TCUPS), or its fill ends in a tail of a few busy warps; and about four
 // chunks per worker keep the pipeline of H2D / kernels / D2H and the balance between workers.  The count is
-// rounded up to a multiple of `workers`, and no chunk gets more than 2^17 pairs (a batch sorted by length
+// rounded to the nearest multiple of `workers`, and no chunk gets more than 2^17 pairs (a batch sorted by length
 // would otherwise put millions of short pairs into one chunk).
 constexpr double CHUNK_MIN_CELLS = 1.3e10, CHUNK_MAX_CELLS = 2.6e10;
 constexpr size_t CHUNK_MAX_PAIRS = size_t(1) << 17;
@@ -1234,7 +1234,7 @@ static void plan_chunks(size_t npairs, const uint64_t* a_off, const uint64_t* b_
     const double total = range_cells(a_off, b_off, 0, npairs);
     const double target = std::min(CHUNK_MAX_CELLS, std::max(CHUNK_MIN_CELLS, total / (4.0 * (double)workers)));
     size_t n = std::max<size_t>(1, (size_t)std::llround(total / target));
-    if(n > 1 || workers > 1) n = (n + workers - 1) / workers * workers;
+    if(n > 1 || workers > 1) n = std::max(workers, (n + workers / 2) / workers * workers);  // nearest multiple
     n = std::min(n, std::max<size_t>(npairs, 1));
     std::vector<std::pair<size_t, size_t>> r;
     std::vector<double> c;
