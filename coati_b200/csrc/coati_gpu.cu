@@ -27,6 +27,7 @@
 #include "viterbi_pipe.cuh"
 #include "viterbi_pipe1.cuh"
 #include "viterbi_pipe3.cuh"
+#include "viterbi_wave1.cuh"
 
 using namespace coati_gpu;
 
@@ -262,7 +263,10 @@ PipeCfg make_cfg(bool ab) {
 }
 template <int R, bool WAVE, int NC>
 PipeCfg make_cfg1() {  // K = 1: FADD2 specialisation, inter-pair (WAVE = false) or intra-pair wavefront
-    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, false, nullptr, viterbi_pipe1_kernel<R, WAVE, NC>,
+    pipe1_kernel_t fn = nullptr;
+    if constexpr(WAVE) fn = viterbi_wave1_kernel<R, NC>;
+    else fn = viterbi_pipe1_kernel<R, NC>;
+    return PipeCfg{1u, (uint32_t)R, WAVE, (uint32_t)NC, false, nullptr, fn,
                    (size_t)PIPE_WARPS * ((R + 3) / 4) * NC * 32 * sizeof(float4)};
 }
 template <int R, int NC>
@@ -355,6 +359,11 @@ struct coati_gpu_batch {
 };
 
 // ---------------------------------------------------------------------------------------------
+#ifdef COATI_WAVE_TRACE
+extern "C" int coati_gpu_debug_wave_trace(unsigned long long* out, size_t n) {
+    return (int)cudaMemcpyFromSymbol(out, g_wave_trace, n * sizeof(unsigned long long));
+}
+#endif
 extern "C" const char* coati_gpu_strerror(int code) {
     switch(code) {
     case COATI_GPU_OK: return "success";
@@ -636,10 +645,15 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
             const bool small_batch = npairs < 2048;
             if(k == 1 && !ctx->no_wave && la >= 1024 && lb >= 512 &&
                (cells >= (1ull << 26) || (small_batch && cells >= (1ull << 21)))) {
-                // measured on B200 (tools/wave_exp.py, tools/long_pair.py): the systolic chain is latency
-                // bound per step, so wide lane tiles win once there are enough bands to fill the GPU:
-                // fill + traceback at 40k: 18.4 ms (R = 4) / 21.0 (R = 10); at 160k: 99 / 91 (R = 8) / 86
-                d.cfg = (la <= 100000 ? 4u : 10u) | CFG_WAVE;
+                // One band = one warp, and the chain of bands runs at the pace of its slowest member, so every band
+                // wants a scheduler of its own (4 per SM): the narrowest lane tile whose band count still fits.
+                // Fill time = (lb + bands * lag) steps; measured on B200 (tools/wave_lag.py, tools/wave_exp.py):
+                // a step costs 139 / 177 / 299 / 333 cycles at R = 2 / 4 / 8 / 10 and a band starts 13 000 / 16 700 /
+                // 20 800 / 23 100 cycles after the one above it; 20k: 2.8 / 3.8 / 4.1 ms at R = 4 / 8 / 10,
+                // 80k: 15.6 / 15.3 / 16.6, 160k: 46.7 / 46.9 / 33.4 (R = 4 and 8 double up on schedulers there).
+                const uint64_t slots = 4ull * (uint64_t)ctx->prop.multiProcessorCount;
+                const uint32_t wr = (la + 127) / 128 <= slots ? 4u : (la + 255) / 256 <= slots ? 8u : 10u;
+                d.cfg = wr | CFG_WAVE;
                 if(ctx->wave_r) d.cfg = ctx->wave_r | CFG_WAVE;
             }
         }
@@ -959,6 +973,7 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                     const uint32_t cap = (uint32_t)ctx->prop.multiProcessorCount * ctx->ctas_per_sm[pc - g_pipe_cfgs];
                     if(pc->wave) {
                         const uint32_t nb = (d.la + 32 * pc->R - 1) / (32 * pc->R);
+                        // CTAs of four warps, one band per scheduler (CTAs of one or two warps measured: no gain)
                         const uint32_t grid = std::min((nb + PIPE_WARPS - 1) / PIPE_WARPS, cap);
                         pc->fn1<<<grid, PIPE_WARPS * 32, pc->smem, sf>>>(
                             bt->d_pairs.p, r.first, r.last, bt->d_counters.p + ri, bt->d_a.p, bt->d_b.p,

@@ -7,8 +7,9 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 NC = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 WAVE = sys.argv[3] if len(sys.argv) > 3 else "false"
-kern = os.environ.get("KERNEL", "viterbi_pipe1_kernel<%d, %s, %d>" % (R, WAVE, NC))
-hdr = os.environ.get("HEADER", "viterbi_pipe1.cuh")
+wave = WAVE == "true"
+kern = os.environ.get("KERNEL", ("viterbi_wave1_kernel<%d, %d>" if wave else "viterbi_pipe1_kernel<%d, %d>") % (R, NC))
+hdr = os.environ.get("HEADER", "viterbi_wave1.cuh" if wave else "viterbi_pipe1.cuh")
 src = '#include "%s/coati_b200/csrc/%s"\nnamespace coati_gpu { template __global__ void %s(const PairDesc*, uint32_t, uint32_t, unsigned int*, const uint8_t*, const uint8_t*, const float*, GapConsts, float4*, uint32_t, uint8_t*, PairResult*, const unsigned int*); }\n' % (root, hdr, kern)
 d = tempfile.mkdtemp()
 open(d + "/k.cu", "w").write(src)

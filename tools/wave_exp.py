@@ -4,7 +4,8 @@ import numpy as np, coati_b200, oracle
 from coati_b200.capi import PackedPairs
 from tests import util
 T = util.load_tables()["mg_golden"]
-for name in ("example-10k", "example-40k", "example-160k"):
+names = sys.argv[1:] or ("example-10k", "example-40k", "example-160k")
+for name in names:
     (_, anc), (_, des) = util.load_fasta(name)
     anc = util.sanitise_ancestor(anc)
     a, b = oracle.encode_pair(anc, des)
