@@ -309,14 +309,14 @@ uint64_t wave_bnd_f4(uint32_t la, uint32_t lb, uint32_t R) {
     return (nb + 1) * ((lb + 4) / 2);
 }
 
-// issue-slot model of one pair on one warp: bands x steps x instructions per step (SASS counts of the
-// step loops, tools/sass_count.py: 108 / 179 / 217 at R = 4 / 8 / 10), weighted by the issue efficiency the
-// resident warps of that configuration reach (8 / 5 / 4 CTAs per SM); checked against whole-workload runs
-// of each configuration alone: 1004 / 963 / 1065 GCUPS on C5
+// issue-slot model of one pair on one warp: bands x steps x instructions per step (SASS counts of the interior
+// step loops, tools/sass_count.py: 85 / 156.5 / 192.5 at R = 4 / 8 / 10, i.e. 14 + 17.9 R), weighted by the issue
+// efficiency of that configuration; checked against whole-workload runs of each configuration alone
+// (COATI_GPU_FORCE_R: 1007 / 1042 / 1137 GCUPS on C5, which the model reproduces with R = 4 at 0.965 of the others)
 double pipe_cost(uint32_t la, uint32_t lb, uint32_t R) {
     const double nbands = (la + 32 * R - 1) / (32 * R);
-    const double eff = R <= 4 ? 0.81 : 0.70;  // measured per-configuration C5 runs (COATI_GPU_FORCE_R)
-    return nbands * (lb + 31.0) * (R * 18.0 + 35.0) / eff;
+    const double eff = R <= 4 ? 0.965 : 1.0;
+    return nbands * (lb + 31.0) * (R * 17.9 + 14.0) / eff;
 }
 
 }  // namespace

@@ -41,6 +41,14 @@ __device__ __forceinline__ void push_sign(uint32_t& acc, float d) {
     acc = __funnelshift_l(__float_as_uint(d), acc, 1);
 }
 
+// A symbol of the descendant, loaded NOW into a register that is then kept: with a plain `b[i]` the compiler
+// re-loads the byte at the point of use instead (the pointer is const __restrict__).
+__device__ __forceinline__ uint32_t ld_symbol_now(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // Sign-shift form of a row PAIR: the five decisions of both rows are the sign bits of
 // five packed subtractions, pushed into the plane accumulators by funnel shifts -- 1.5 instructions per
 // decision bit instead of FSETP + predicated IMAD.  Planes 0-3 are accumulated inverted (bit = "differs

@@ -19,6 +19,11 @@
 
 namespace coati_gpu {
 
+#ifndef COATI_PIPE1_UNROLL
+#define COATI_PIPE1_UNROLL 4
+#endif
+constexpr int PIPE1_UNROLL = COATI_PIPE1_UNROLL;  // steps per basic block in the interior blocks
+
 // Inter-pair scheme: one warp per pair, the bands of a pair processed one after another by the same warp (pairs
 // [first, last) pulled from `counter`).  The intra-pair wavefront for long single pairs is viterbi_wave1.cuh.
 // NC = substitution-table columns kept per lane: 16 (all IUPAC codes) or 4 when no descendant of the
@@ -27,8 +32,13 @@ namespace coati_gpu {
 // nc_flag (raw-sequence batches): device word set by encode_pairs_kernel when any descendant carries an
 // ambiguity code; both NC variants are launched and the one that does not apply returns at once, so the
 // host never waits for the flag.
+#ifndef COATI_PIPE1_MINB8
+#define COATI_PIPE1_MINB8 4
+#endif
+// resident CTAs per SM the register allocation aims at: 4 (128 registers) for the 10-row lane tile
+constexpr int pipe1_min_ctas(int R) { return R == 8 ? COATI_PIPE1_MINB8 : 4; }
 template <int R, int NC>
-__global__ void __launch_bounds__(PIPE_WARPS * 32)
+__global__ void __launch_bounds__(PIPE_WARPS * 32, pipe1_min_ctas(R))
 viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
@@ -116,6 +126,45 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             // blocks of 32 steps = one word of every decision plane; the flush sits between blocks
             for(uint32_t t0 = 0; t0 < nsteps; t0 += 32) {
               const uint32_t t1 = min(t0 + 32u, nsteps);
+              if(PIPE1_UNROLL > 0 && t0 >= 32u && t0 + 33u <= lb) {
+                // ---- all 32 lanes are inside the lattice for the whole block: no activity test, every lane loads
+                // its own symbol (one step ahead), pointers run with immediate offsets, four steps to a basic block
+                const uint8_t* ps = b + t0 - lane;          // ps[i]: this lane's symbol on step t0 + i
+                const float2* pw = bin + t0 + 2;            // pw[i]: lane 0's inputs for step t0 + i + 1
+                float2* pst = bout + t0 + 1 - lane;         // pst[i]: lane 31's cell of step t0 + i
+                uint32_t off = ld_symbol_now(ps) * 512u;
+#pragma unroll 1
+                for(int grp = 0; grp < 32 / (PIPE1_UNROLL > 0 ? PIPE1_UNROLL : 1); ++grp, ps += PIPE1_UNROLL, pw += PIPE1_UNROLL, pst += PIPE1_UNROLL) {
+#pragma unroll
+                    for(int i = 0; i < PIPE1_UNROLL; ++i) {
+                        const float recvX = __shfl_sync(FULL, outX, rot);
+                        const float recvY = __shfl_sync(FULL, outY, rot);
+                        const float2 bnv = pw[i];
+                        const uint32_t s1 = ld_symbol_now(ps + i + 1);
+                        float sv[R4 * 4];
+#pragma unroll
+                        for(int h = 0; h < R4; ++h) {
+                            const float4 v = *reinterpret_cast<const float4*>(tab_lane + off + h * (NC * 512));
+                            sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
+                        }
+                        float D = recvY;
+                        float Mv[R];
+                        Mv[0] = diagX + sv[0];
+#pragma unroll
+                        for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
+#pragma unroll
+                        for(int q = 0; q < R; q += 2) COATI_ROWPAIR_SGN(q)
+                        diagX = recvX;
+                        if(lane == 31) pst[i] = make_float2(Xp[R - 1], D);
+                        outX = lane == 31 ? bnv.x : Xp[R - 1];
+                        outY = lane == 31 ? bnv.y : D;
+                        boff = off;  // what the lane below receives on the next step, should an edge block follow
+                        off = s1 * 512u;
+                    }
+                }
+                if(lane == 31) boff = (uint32_t)b[t0 + 32] * 512u;  // lane 31 hands lane 0 the symbol of ITS next step
+                u += 32;
+              } else {
               const float2* pbin = bin + t0 + 2;  // lane 0's inputs for the NEXT step (column t + 2);
               const uint8_t* pb = b + t0 + 1;     // both arrays are padded past column lb
               for(uint32_t t = t0; t < t1; ++t, ++u) {
@@ -148,6 +197,7 @@ viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                     outX = bnv.x, outY = bnv.y;
                     boff = bl * 512u;
                 }
+              }
               }
               // ---- flush the 32-step block of decision planes ---------------------------------
               {

@@ -51,7 +51,7 @@ namespace coati_gpu {
     }
 
 template <int R, int NC>
-__global__ void __launch_bounds__(PIPE_WARPS * 32)
+__global__ void __launch_bounds__(PIPE_WARPS * 32, 4)  // 128 registers: four CTAs per SM
 viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
@@ -180,8 +180,58 @@ viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                 }
                 ++u;
             };
+            // The same step for blocks in which all 32 lanes are inside the lattice (viterbi_pipe1.cuh): no activity
+            // test, every lane loads its own symbol one step ahead, pointers with immediate offsets, a whole ring
+            // turn (three steps) to a basic block.
+            const uint8_t* ps = b;
+            const float4* pw = bin;
+            float4* pst = bout;
+            uint32_t off = 0;
+            auto fstep = [&](auto zs_c, int i) {
+                constexpr int ZS = decltype(zs_c)::value;
+                const float recvX = __shfl_sync(FULL, outX, rot);
+                recvY[0] = __shfl_sync(FULL, outY0, rot);
+                recvY[1] = __shfl_sync(FULL, outY1, rot);
+                recvY[2] = __shfl_sync(FULL, outY2, rot);
+                const float4 bnv = pw[i];
+                const uint32_t s1 = ld_symbol_now(ps + i + 1);
+                float sv[R4 * 4];
+#pragma unroll
+                for(int h = 0; h < R4; ++h) {
+                    const float4 v = *reinterpret_cast<const float4*>(tab_lane + off + h * (NC * 512));
+                    sv[4 * h] = v.x, sv[4 * h + 1] = v.y, sv[4 * h + 2] = v.z, sv[4 * h + 3] = v.w;
+                }
+                float Mv[R];
+                Mv[0] = diagX + sv[0];
+#pragma unroll
+                for(int q = 1; q < R; ++q) Mv[q] = Xp[q - 1] + sv[q];
+#pragma unroll
+                for(int q = 0; q < R; q += 2) COATI_ROWPAIR3_SGN(q, ZS)
+                diagX = recvX;
+                if(lane == 31) pst[i] = make_float4(Xp[R - 1], Ycur[R - 3], Ycur[R - 2], Ycur[R - 1]);
+                outX = lane == 31 ? bnv.x : Xp[R - 1];
+                outY0 = lane == 31 ? bnv.y : Ycur[R - 3];
+                outY1 = lane == 31 ? bnv.z : Ycur[R - 2];
+                outY2 = lane == 31 ? bnv.w : Ycur[R - 1];
+                boff = off;  // what the lane below receives on the next step, should an edge block follow
+                off = s1 * 512u;
+            };
             for(uint32_t t0 = 0; t0 < nsteps; t0 += BS) {
                 const uint32_t tn = min(BS, nsteps - t0);
+                if(t0 >= 32u && t0 + BS + 1 <= lb) {
+                    ps = b + t0 - lane;       // ps[i]: this lane's symbol on step t0 + i
+                    pw = bin + t0 + 2;        // pw[i]: lane 0's inputs for step t0 + i + 1
+                    pst = bout + t0 + 1 - lane;  // pst[i]: lane 31's cell of step t0 + i
+                    off = ld_symbol_now(ps) * 512u;
+#pragma unroll 1
+                    for(uint32_t tt = 0; tt < BS; tt += 3, ps += 3, pw += 3, pst += 3) {
+                        fstep(std::integral_constant<int, 0>{}, 0);
+                        fstep(std::integral_constant<int, 1>{}, 1);
+                        fstep(std::integral_constant<int, 2>{}, 2);
+                    }
+                    if(lane == 31) boff = (uint32_t)b[t0 + BS] * 512u;  // lane 31 hands lane 0 the symbol of ITS next step
+                    u += BS, pbin += BS, pb += BS;
+                } else
                 for(uint32_t tt = 0; tt < tn; tt += 3) {
                     step(std::integral_constant<int, 0>{});
                     if(tt + 1 < tn) step(std::integral_constant<int, 1>{});

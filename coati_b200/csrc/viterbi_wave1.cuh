@@ -49,13 +49,6 @@ __device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
     asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
 }
-// A symbol of the descendant, loaded NOW into a register that is then kept: with a plain `b[i]` the compiler
-// re-loads the byte at the point of use instead (the pointer is const __restrict__).
-__device__ __forceinline__ uint32_t ld_symbol_now(const uint8_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 // The producer's side of the hand-off: one 64-bit relaxed store at gpu scope (a plain weak store racing with the
 // relaxed polls would be a data race under the PTX memory model; weak / volatile / write-through stores and an
 // L2 exchange were measured: the first three change nothing, the exchange doubles the step).  Predicated inside

@@ -13,7 +13,7 @@ hdr = os.environ.get("HEADER", "viterbi_wave1.cuh" if wave else "viterbi_pipe1.c
 src = '#include "%s/coati_b200/csrc/%s"\nnamespace coati_gpu { template __global__ void %s(const PairDesc*, uint32_t, uint32_t, unsigned int*, const uint8_t*, const uint8_t*, const float*, GapConsts, float4*, uint32_t, uint8_t*, PairResult*, const unsigned int*); }\n' % (root, hdr, kern)
 d = tempfile.mkdtemp()
 open(d + "/k.cu", "w").write(src)
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-cubin", "-Xptxas", "-v", "-o", d + "/k.cubin", d + "/k.cu"])
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false"] + os.environ.get("DEFS", "").split() + ["-cubin", "-Xptxas", "-v", "-o", d + "/k.cubin", d + "/k.cu"])
 sass = subprocess.check_output(["cuobjdump", "-sass", d + "/k.cubin"]).decode()
 ins = []
 for l in sass.split("\n"):
@@ -32,3 +32,8 @@ print("step loop", hex(best[0]), hex(best[1]), len(body), "instructions")
 print(sorted(c.items(), key=lambda kv: -kv[1]))
 if os.environ.get("DUMP"):
     for a, t in body: print(hex(a), t)
+if os.environ.get("ALL"):
+    for ab in loops:
+        bd = [(a, t) for a, t in ins if ab[0] <= a <= ab[1]]
+        cc = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for a, t in bd)
+        print(hex(ab[0]), len(bd), sorted(cc.items(), key=lambda kv: -kv[1])[:14])
