@@ -42,7 +42,7 @@ LANES_PER_SM = 128          # FP32 lanes per SM per clock
 WORKLOADS = {
     "c5": dict(id=5, k=1, table="mg_c5", pairs=1_000_000, seed=42,
                model=dict(model="mar-mg", br_len=0.05, omega=0.5, pi=(0.25, 0.25, 0.25, 0.25)),
-               kernel="viterbi_pipe1_kernel<10,false,4>",
+               kernel="viterbi_pipe1_kernel<10,4>",
                desc="BASELINE configs[4]: length-binned pairs {150,300,600,1200,2400} nt "
                     "(40/30/20/8/2 %), mar-mg w=0.5 pi=0.25 t=0.05, k=1"),
     "c4": dict(id=4, k=3, table="ecm_default", pairs=100_000, seed=20240603,

@@ -153,9 +153,17 @@ struct coati_gpu_ctx {
     // their 2400-nt pairs, 2 ms of a 12 ms fill at 32 k pairs -- is covered, and there are never three fills
     // competing from the start.  Measured on C5, 1 M pairs cut into 31 sub-batches: one stream per lane (round 1)
     // 377-490 ms with convoys, one shared stream 410-490 ms (tails exposed), two alternating streams 326 ms.
-    static constexpr int NLANE = 3;
+    // Four lanes: two fills share the GPU and end together, the third follows at once, so with three lanes all
+    // three sub-batches in flight completed within a few ms of each other and the GPU idled while the host
+    // planned and uploaded the next one (host timeline, COATI_GPU_TRACE: 76 ms per three 23 ms sub-batches);
+    // a fourth lane keeps one sub-batch queued behind them: 1 M pairs 330-341 -> 319 ms (3 / 4 / 5 lanes: 341 /
+    // 319 / 327 ms in one session).
+#ifndef COATI_GPU_NLANE
+#define COATI_GPU_NLANE 4
+#endif
+    static constexpr int NLANE = COATI_GPU_NLANE;
     cudaStream_t fill_stream = nullptr, fill_stream2 = nullptr;
-    cudaStream_t lane_hi[NLANE] = {nullptr, nullptr, nullptr};
+    cudaStream_t lane_hi[NLANE] = {};
     cudaDeviceProp prop{};
     bool model_set = false;
     GapConsts gap{};
@@ -1318,10 +1326,9 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
     const size_t npairs = A.npairs;
     const uint64_t *a_off = A.a_off, *b_off = A.b_off;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    constexpr int NSLOT = 3;  // sub-batches in flight: one finishing, one filling, one queued behind it
-    coati_gpu_batch* bt[NSLOT] = {nullptr, nullptr, nullptr};
-    size_t first[NSLOT] = {0, 0, 0};
-    static_assert(NSLOT == coati_gpu_ctx::NLANE, "one lane per slot");
+    constexpr int NSLOT = coati_gpu_ctx::NLANE;  // sub-batches in flight, one lane per slot
+    coati_gpu_batch* bt[NSLOT] = {};
+    size_t first[NSLOT] = {};
     // raw pairs: the per-pair scan (length checks, end stops) runs range by range, inside the pipeline
     std::vector<uint8_t> rawbuf;
     // direction-stream budget of a lane, from the memory free now (the GPU is idle: cheap call)

@@ -32,13 +32,16 @@ constexpr int PIPE1_UNROLL = COATI_PIPE1_UNROLL;  // steps per basic block in th
 // nc_flag (raw-sequence batches): device word set by encode_pairs_kernel when any descendant carries an
 // ambiguity code; both NC variants are launched and the one that does not apply returns at once, so the
 // host never waits for the flag.
-#ifndef COATI_PIPE1_MINB8
-#define COATI_PIPE1_MINB8 4
+// Register budget: 128 = four CTAs per SM (the four-step block would take 143 and drop to three).  Four CTAs of
+// 128 x 128 registers fill the register file, and the fills are persistent, so the short kernels of the neighbouring
+// sub-batches (traceback, expansion, encode) get onto an SM only as CTAs of a fill retire; with four pipeline lanes
+// that costs nothing measurable end to end (1 M pairs: 319-320 ms at 128 registers, 314-330 ms at 120, fills alone
+// 303 / 309 ms), so the faster fill is kept.
+#ifndef COATI_PIPE1_REGS
+#define COATI_PIPE1_REGS 128
 #endif
-// resident CTAs per SM the register allocation aims at: 4 (128 registers) for the 10-row lane tile
-constexpr int pipe1_min_ctas(int R) { return R == 8 ? COATI_PIPE1_MINB8 : 4; }
 template <int R, int NC>
-__global__ void __launch_bounds__(PIPE_WARPS * 32, pipe1_min_ctas(R))
+__global__ void __maxnreg__(COATI_PIPE1_REGS)
 viterbi_pipe1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,

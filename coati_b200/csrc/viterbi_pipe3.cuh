@@ -51,7 +51,7 @@ namespace coati_gpu {
     }
 
 template <int R, int NC>
-__global__ void __launch_bounds__(PIPE_WARPS * 32, 4)  // 128 registers: four CTAs per SM
+__global__ void __maxnreg__(COATI_PIPE1_REGS)  // see viterbi_pipe1.cuh
 viterbi_pipe3_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
                      unsigned int* __restrict__ counter, const uint8_t* __restrict__ a_all,
                      const uint8_t* __restrict__ b_all, const float* __restrict__ table, GapConsts g,
