@@ -1311,7 +1311,7 @@ static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* 
     };
     int rc = run(nsub);
     if(rc == COATI_GPU_E_NOMEM) {
-        // a lane owns a third of the memory: a pair too big for that may still fit the whole device; and
+        // a lane owns its share (1 / NLANE) of the memory: a pair too big for that may still fit the whole device; and
         // idle pool blocks of earlier calls are given back before the plan is redone from the memory
         // that is free now
         CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1471,7 +1471,7 @@ extern "C" int coati_gpu_alignpair_batch(coati_gpu_ctx* ctx, size_t npairs, cons
 // ---- one batch over several devices ------------------------------------------------------------------
 // north_star (4) / SURVEY 8(e): independent pairs sharded over the GPUs of one box by length-binned work
 // queues.  The batch is cut into contiguous chunks, ordered heaviest first, and one host thread per context
-// runs the three-lane pipeline of the single-device call on whatever chunk it pops next; inside a chunk the
+// runs the four-lane pipeline of the single-device call on whatever chunk it pops next; inside a chunk the
 // planner bins the pairs by kernel configuration and lattice size as always.  Results land in the caller's
 // arenas in input order -- no collective, no second copy.
 extern "C" int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n_ctx, size_t npairs,
