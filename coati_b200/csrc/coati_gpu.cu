@@ -1215,6 +1215,9 @@ struct BatchArgs {
     const uint32_t* model;
 };
 
+#ifndef COATI_GPU_TAIL_SPLIT
+#define COATI_GPU_TAIL_SPLIT 1
+#endif
 struct RangeQueue {
     std::vector<std::pair<size_t, size_t>> ranges;  // [first, last) in pair indices
     std::atomic<size_t> next{0};
@@ -1228,6 +1231,7 @@ struct RangeQueue {
         p0 = ranges[j].first, p1 = ranges[j].second;
         return true;
     }
+    bool drained() const { return next.load(std::memory_order_relaxed) >= ranges.size(); }
     void add(size_t p0, size_t p1, const uint64_t* a_off, const uint64_t* b_off) {
         ranges.emplace_back(p0, p1);
         max_sym = std::max<uint64_t>(max_sym, (a_off[p1] - a_off[p0]) + (b_off[p1] - b_off[p0]));
@@ -1390,6 +1394,11 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
         }
         if(!q.pop(p0, p1)) return false;
         if(j == 0 && pipelined && p1 - p0 > 2 * HEAD_PAIRS) rest0 = p0 + HEAD_PAIRS, rest1 = p1, p1 = rest0;
+        // ... and so is the last one: what is left to do after the last fill -- the traceback, the expansion and
+        // the D2H copy of its rows -- then belongs to a third of a chunk (its fill shares the GPU with the fill
+        // of the other two thirds)
+        else if(COATI_GPU_TAIL_SPLIT && pipelined && q.drained() && p1 - p0 > 8 * HEAD_PAIRS)
+            rest0 = p0 + (p1 - p0) / 3 * 2, rest1 = p1, p1 = rest0;
         return true;
     };
     for(size_t j = 0; rc == COATI_GPU_OK && next_range(j); ++j) {
