@@ -1397,7 +1397,7 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
         // ... and so is the last one: what is left to do after the last fill -- the traceback, the expansion and
         // the D2H copy of its rows -- then belongs to a third of a chunk (its fill shares the GPU with the fill
         // of the other two thirds)
-        else if(COATI_GPU_TAIL_SPLIT && pipelined && q.drained() && p1 - p0 > 8 * HEAD_PAIRS)
+        else if(COATI_GPU_TAIL_SPLIT && pipelined && q.drained() && p1 - p0 > 3 * HEAD_PAIRS)
             rest0 = p0 + (p1 - p0) / 3 * 2, rest1 = p1, p1 = rest0;
         return true;
     };
