@@ -16,13 +16,13 @@ __device__ __forceinline__ f2 mk2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ float lo2(f2 a) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    float lo;
+    asm("mov.b64 {%0, _}, %1;" : "=f"(lo) : "l"(a.v));
     return lo;
 }
 __device__ __forceinline__ float hi2(f2 a) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    float hi;
+    asm("mov.b64 {_, %0}, %1;" : "=f"(hi) : "l"(a.v));
     return hi;
 }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) {  // two independent round-to-nearest FADDs

@@ -226,7 +226,7 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         // loaded at the start of this one
         uint32_t symc[WAVE_U], symn[WAVE_U];
 #pragma unroll
-        for(uint32_t i = 0; i < WAVE_U; ++i) symn[i] = ld_symbol_now(b + sym_idx(1 + i));
+        for(uint32_t i = 0; i < WAVE_U; ++i) symc[i] = 0, symn[i] = ld_symbol_now(b + sym_idx(1 + i));
         const uint8_t* b_lane = b - lane;  // b_lane[t] is this lane's symbol on step t
 
         // ---- one step ----------------------------------------------------------------------------------
