@@ -16,15 +16,22 @@
 // tools/sass_sched.py).  Round 2's first wavefront shared viterbi_pipe1's loop: 298 cycles per step at R = 4
 // (485 at R = 10) and a lag of 85 steps per band.  What this file does about both:
 //   * nothing but the recurrence sits on the step's dependent chain.  The symbols do not depend on the fill, so
-//     each lane loads its own descendant symbol two steps ahead (L1) and its substitution scores one step ahead
-//     (shared memory); the old loop passed the symbol down the lanes by shuffle and then waited for the LDS.
-//   * steps in which all 32 lanes are inside the lattice (all but the first 31 and the last 33) run without
-//     the per-lane activity test, four to a basic block, so the sign pushes of one step (a third of its
-//     instructions, off the chain) fill the shuffle latency of the next.
+//     each lane loads its own descendant symbol a group (four steps) ahead (L1) and its substitution scores one
+//     step ahead (shared memory); the old loop passed the symbol down the lanes by shuffle and then waited for
+//     the LDS.
+//   * EVERY lane computes on EVERY step, inside the lattice or not (see `step`): a step is one basic block without
+//     an activity test, four of them are scheduled together, and the sign pushes of one step (a third of its
+//     instructions, off the chain) fill the shuffle latency of the next.  The first and last blocks of a band --
+//     lanes entering and leaving the lattice -- are on the critical path of the whole wavefront and cost three
+//     selects per row more, nothing else.
 //   * the row above reaches lane 0 through a rolling window: lane j holds column j (mod 32); every four steps
-//     four lanes fetch the columns needed WAVE_D + 2 steps later (relaxed L2 loads into registers of their own,
-//     not waited for), the fetch of two groups ago is taken over and the four columns about to be used are
-//     checked (re-polled only if the producer has not got there).
+//     four lanes fetch the columns needed WAVE_D steps later (relaxed L2 loads into registers of their own, not
+//     waited for), the fetch of three groups ago enters the window and the vote on the next group's columns is
+//     issued a group before it is branched on (re-polled only if the producer has not got there).
+//   * one band per scheduler: the host picks the narrowest lane tile whose band count fits 4 x SMs.
+// Measured (B200, tools/wave_lag.py): 139 / 177 / 299 / 333 cycles per step at R = 2 / 4 / 8 / 10; fills of the
+// sampledata pairs 10k / 40k / 160k: 1.39 / 5.8 / 33.3 ms (2.36 / 9.8 / 47 before).  DESIGN.md 4.2 has the evidence
+// and the list of what was measured and dropped.
 #pragma once
 
 #include <type_traits>
