@@ -656,11 +656,12 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
                 // One band = one warp, and the chain of bands runs at the pace of its slowest member, so every band
                 // wants a scheduler of its own (4 per SM): the narrowest lane tile whose band count still fits.
                 // Fill time = (lb + bands * lag) steps; measured on B200 (tools/wave_lag.py, tools/wave_exp.py):
-                // a step costs 139 / 177 / 299 / 333 cycles at R = 2 / 4 / 8 / 10 and a band starts 13 000 / 16 700 /
-                // 20 800 / 23 100 cycles after the one above it; 20k: 2.8 / 3.8 / 4.1 ms at R = 4 / 8 / 10,
-                // 80k: 15.6 / 15.3 / 16.6, 160k: 46.7 / 46.9 / 33.4 (R = 4 and 8 double up on schedulers there).
+                // a step costs 109 / 164 / 277 / 332 cycles at R = 2 / 4 / 8 / 10 and the fill grows by 9 000 / 12 000 /
+                // 21 400 / 24 600 cycles per band; fills at R = 2 / 4 / 8 / 10: 10k 1.13 / 1.27 / 1.88 / 2.04 ms,
+                // 20k 2.35 / 2.55 / 3.69 / 4.07, 40k 6.28 / 5.20 / 7.44 / 8.27, 80k 17.8 / 15.0 / 14.8 / 16.6,
+                // 160k 64.9 / 47.3 / 47.0 / 33.2 (too many bands double up on schedulers).
                 const uint64_t slots = 4ull * (uint64_t)ctx->prop.multiProcessorCount;
-                const uint32_t wr = (la + 127) / 128 <= slots ? 4u : (la + 255) / 256 <= slots ? 8u : 10u;
+                const uint32_t wr = (la + 63) / 64 <= slots ? 2u : (la + 127) / 128 <= slots ? 4u : (la + 255) / 256 <= slots ? 8u : 10u;
                 d.cfg = wr | CFG_WAVE;
                 if(ctx->wave_r) d.cfg = ctx->wave_r | CFG_WAVE;
             }

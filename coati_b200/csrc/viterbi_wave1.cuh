@@ -24,13 +24,13 @@
 //     instructions, off the chain) fill the shuffle latency of the next.  The first and last blocks of a band --
 //     lanes entering and leaving the lattice -- are on the critical path of the whole wavefront and cost three
 //     selects per row more, nothing else.
-//   * the row above reaches lane 0 through a rolling window: lane j holds column j (mod 32); every four steps
-//     four lanes fetch the columns needed WAVE_D steps later (relaxed L2 loads into registers of their own, not
-//     waited for), the fetch of three groups ago enters the window and the vote on the next group's columns is
-//     issued a group before it is branched on (re-polled only if the producer has not got there).
+//   * the row above reaches lane 0 through a rolling window: lane j holds column j (mod 32); every group (eight
+//     steps; four for the widest tile) as many lanes fetch the columns needed WAVE_D steps later (relaxed L2 loads
+//     into registers of their own, not waited for), an earlier fetch enters the window and the vote on the next
+//     group's columns is issued a group before it is branched on (re-polled only if the producer has not got there).
 //   * one band per scheduler: the host picks the narrowest lane tile whose band count fits 4 x SMs.
-// Measured (B200, tools/wave_lag.py): 139 / 177 / 299 / 333 cycles per step at R = 2 / 4 / 8 / 10; fills of the
-// sampledata pairs 10k / 40k / 160k: 1.39 / 5.8 / 33.3 ms (2.36 / 9.8 / 47 before).  DESIGN.md 4.2 has the evidence
+// Measured (B200, tools/wave_lag.py): 108 / 163 / 274 / 331 cycles per step at R = 2 / 4 / 8 / 10; fills of the
+// sampledata pairs 10k / 40k / 160k: 1.13 / 5.2 / 33.2 ms (2.36 / 9.8 / 47 before).  DESIGN.md 4.2 has the evidence
 // and the list of what was measured and dropped.
 #pragma once
 
@@ -41,14 +41,15 @@
 
 namespace coati_gpu {
 
-#ifndef COATI_WAVE_D
-#define COATI_WAVE_D 12
-#endif
+// Steps per group (one window update, one basic block) and how far ahead of its use a column of the row above is
+// fetched.  Eight-step groups halve the window overhead and give ptxas more to interleave: modelled 141 instead of
+// 164 cycles per step at R = 4 (97 / 129 at R = 2, 244 / 277 at R = 8), measured 164 / 177 (109 / 139, 277 / 299);
+// the widest tile gains nothing in the step (332) and loses in the lag (24.6 -> 30.9 k cycles), so it keeps four.
+__host__ __device__ constexpr uint32_t wave_group(int R) { return R >= 10 ? 4u : 8u; }
+__host__ __device__ constexpr uint32_t wave_ahead(int R) { return R >= 10 ? 12u : 16u; }  // three groups of four / two groups of eight
 #ifndef COATI_WAVE_SLEEP
 #define COATI_WAVE_SLEEP 20  // ns between polls of a column the producer has not written yet (0 / 20 / 40 measured: no difference)
 #endif
-constexpr uint32_t WAVE_D = COATI_WAVE_D;  // how far ahead of its use a column of the row above is fetched, in steps
-constexpr uint32_t WAVE_U = 4;             // steps per group (one window update, one basic block)
 
 // The consumer's side of the hand-off: a relaxed load at gpu scope (L2), re-issued until the sentinel is gone.
 __device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
@@ -90,7 +91,9 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                      float4* __restrict__ bnd_all, uint32_t bnd_stride, uint8_t* __restrict__ dirs,
                      PairResult* __restrict__ results, const unsigned int* __restrict__ nc_flag) {
     static_assert(R % 2 == 0, "rows are processed in pairs");
-    static_assert(WAVE_D == 3 * WAVE_U, "a fetch enters the window three groups after it was issued");
+    constexpr uint32_t WAVE_U = wave_group(R), WAVE_D = wave_ahead(R);
+    static_assert(WAVE_D == 3 * WAVE_U || WAVE_D == 2 * WAVE_U, "a fetch enters the window two or three groups after it was issued");
+    constexpr bool THREE = WAVE_D == 3 * WAVE_U;  // a fetched register is read one group (>= the L2 round trip) after the load
     constexpr int R4 = (R + 3) / 4;
     constexpr int H = 32 * R;
     constexpr uint32_t WPL = (5 * R + 3) & ~3u;
@@ -194,8 +197,13 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
                 }
             }
             win.x = mine ? pf0.x : win.x, win.y = mine ? pf0.y : win.y;
-            pf0 = pf1, pf1 = pf2;
-            if(wmine(tg + 3 + WAVE_D)) pf2 = ld_relaxed_f2(bin + wcol(tg + 3 + WAVE_D));
+            if(THREE) {
+                pf0 = pf1, pf1 = pf2;
+                if(wmine(tg + 3 + WAVE_D)) pf2 = ld_relaxed_f2(bin + wcol(tg + 3 + WAVE_D));
+            } else {
+                pf0 = pf1;
+                if(wmine(tg + 3 + WAVE_D)) pf1 = ld_relaxed_f2(bin + wcol(tg + 3 + WAVE_D));
+            }
             late = __any_sync(FULL, wmine(tg + 3 + WAVE_U) && pf0.x != pf0.x);
         };
         // lane 31's outgoing registers carry lane 0's inputs, the row above the band: column 1 now, and column
@@ -213,8 +221,8 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
             if(lane == 31) outX = x1, outY = y1;
         }
         if(wmine(3)) pf0 = ld_relaxed_f2(bin + wcol(3));  // columns 3 .. 14: groups 0, 1 and 2
-        if(wmine(7)) pf1 = ld_relaxed_f2(bin + wcol(7));
-        if(wmine(11)) pf2 = ld_relaxed_f2(bin + wcol(11));
+        if(wmine(3 + WAVE_U)) pf1 = ld_relaxed_f2(bin + wcol(3 + WAVE_U));
+        if(THREE && wmine(3 + 2 * WAVE_U)) pf2 = ld_relaxed_f2(bin + wcol(3 + 2 * WAVE_U));
         // ---- symbols a group ahead, substitution scores one step ahead -------------------------------
         // lane l is at column t - l + 1 on step t: symbol b[t - l]; indices are clamped outside the lattice
         auto sym_idx = [&](uint32_t t) {
@@ -250,7 +258,7 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         //   PHASE 2: last blocks: lanes leave the lattice -> guarded boundary store, score
         const uint32_t qsel = rr % R;
         float* const score_out = &results[pd.orig].score;
-        const uint8_t* psym = b_lane + 5;           // psym[t]: this lane's symbol on step t + 5 (PHASE 1: no clamp)
+        const uint8_t* psym = b_lane + WAVE_U + 1;           // psym[t]: this lane's symbol on step t + 5 (PHASE 1: no clamp)
         float2* pst = bout + 1 - (ptrdiff_t)lane;   // pst[t]: where lane 31 puts the bottom row on step t
         auto step = [&](auto phase, uint32_t t, uint32_t i) {  // t = tg + i, i the unrolled index within the group
             constexpr int PHASE = decltype(phase)::value;
@@ -305,7 +313,7 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
 #pragma unroll
                 for(uint32_t i = 0; i < WAVE_U; ++i) {
                     symc[i] = symn[i];
-                    symn[i] = ld_symbol_now(PHASE == 1 ? psym + i : b + sym_idx(tg + 5 + i));
+                    symn[i] = ld_symbol_now(PHASE == 1 ? psym + i : b + sym_idx(tg + WAVE_U + 1 + i));
                 }
 #pragma unroll
                 for(uint32_t i = 0; i < WAVE_U; ++i) step(phase, tg + i, i);
@@ -317,7 +325,7 @@ viterbi_wave1_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_
         // runs its 32 steps too (past step lb + 30 every lane is outside the lattice).  Needs lb >= 34.
         for(uint32_t t0 = 0; t0 < nsteps; t0 += 32) {
             if(t0 == 0) block(std::integral_constant<int, 0>{}, t0);
-            else if(t0 + 40u <= lb) block(std::integral_constant<int, 1>{}, t0);  // inside, and so are the symbols fetched ahead
+            else if(t0 + 36u + WAVE_U <= lb) block(std::integral_constant<int, 1>{}, t0);  // inside, and so are the symbols fetched ahead
             else block(std::integral_constant<int, 2>{}, t0);
             flush(t0);
 #ifdef COATI_WAVE_TRACE
