@@ -343,7 +343,6 @@ def main():
     order = np.argsort(my_first)
     cells_pair = np.diff(a_off).astype(np.float64) * np.diff(b_off).astype(np.float64)
     cells_total = float(cells_pair.sum())
-    my_pairs = int((my_last - my_first).sum())
     my_cells = float(sum(cells_pair[int(f):int(l)].sum() for f, l in zip(my_first, my_last)))
 
     # ---- device-resident metric: the rank's pairs as one local CSR batch ----------------------------------
@@ -426,6 +425,7 @@ def main():
     for _ in range(max(1, args.warmup)):         # warm-up (pool allocations, page faults)
         e2e_once()
     barrier()
+    moved0 = ctx.transfer_bytes
     t0 = time.perf_counter()
     e2e_steps = max(1, args.steps)
     for _ in range(e2e_steps):
@@ -437,9 +437,11 @@ def main():
     clocks = sampler.stop()
     if rank == 0:  # every rank's rows are in the one arena
         assert int((status != 0).sum()) == 0 and int(out_len.min()) > 0, "e2e run failed"
-    h2d = int(sum(int(a_off[int(l)] - a_off[int(f)]) + int(b_off[int(l)] - b_off[int(f)])
-                  for f, l in zip(my_first, my_last)))
-    d2h = int(2 * (h2d + my_pairs) + my_pairs * 32)
+    # bytes per step as the library counted them: symbols + pair descriptors in; result records and rows out (the
+    # rows are written by the expansion kernel straight into the page-locked arena, length + terminator each;
+    # with COATI_GPU_ROWS_DIRECT=0 or a pageable arena it is a copy of the padded slots, 2 (La + Lb + 1) per pair)
+    moved1 = ctx.transfer_bytes
+    h2d, d2h = ((moved1[i] - moved0[i]) // e2e_steps for i in (0, 1))
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
     if dist is not None:
@@ -514,7 +516,10 @@ def main():
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "pairs_per_s": npairs * e2e_steps / e2e_s,
                 "steps": e2e_steps, "ms_per_step_by_rank": [round(x, 2) for x in e2e_rank_ms],
-                "api": "coati_gpu_alignpair_batch_ranges, rows delivered to one host arena"},
+                "api": "coati_gpu_alignpair_batch_ranges, rows delivered to one host arena",
+                "row_delivery": ("expansion kernel writes the used bytes of every row into the page-locked arena"
+                                 if arena_pinned and os.environ.get("COATI_GPU_ROWS_DIRECT", "1") != "0"
+                                 else "D2H copy of the padded slots")},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": {"bound": "fp32_issue", "kernel": wl["kernel"], "achieved": ach_tflops,

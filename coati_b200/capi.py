@@ -50,6 +50,8 @@ def load_library() -> C.CDLL:
     lib.coati_gpu_stream.restype = vp
     lib.coati_gpu_launch_count.argtypes = [vp]
     lib.coati_gpu_launch_count.restype = C.c_uint64
+    lib.coati_gpu_transfer_bytes.argtypes = [vp, _u64p, _u64p]
+    lib.coati_gpu_transfer_bytes.restype = None
     lib.coati_gpu_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.coati_gpu_set_model.argtypes = [vp, _fp, C.c_float, C.c_float, C.c_uint32]
@@ -341,6 +343,13 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.coati_gpu_launch_count(self.h))
+
+    @property
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes moved by the batch calls of this context since creation"""
+        h2d, d2h = C.c_uint64(0), C.c_uint64(0)
+        self.lib.coati_gpu_transfer_bytes(self.h, C.byref(h2d), C.byref(d2h))
+        return int(h2d.value), int(d2h.value)
 
     def device_info(self):
         sm, khz = C.c_int(0), C.c_int(0)

@@ -170,10 +170,18 @@ struct coati_gpu_ctx {
     float* d_table = nullptr;  // n_models x TABLE_ROWS x TABLE_LD
     uint32_t n_models = 1, table_cap = 1;
     uint64_t launches = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the batch calls since creation (coati_gpu_transfer_bytes)
     std::string last_error;
     size_t dir_budget = 0;  // 0 = derive from free memory
     bool force_generic = false, no_wave = false;
     bool tb_serial = false;  // COATI_GPU_TB_SERIAL=1: long pairs walked one column at a time (A/B)
+    // Rows into page-locked caller arenas: written by rows_to_host_kernel (used bytes only: half the volume, but
+    // SM-issued writes) or copied as padded slots by the copy engine.  -1: the kernel when the call is one share of
+    // a batch spread over several devices (their host links are shared and the volume decides: section 5 of
+    // DESIGN.md), the copy when the device has the link to itself (measured at N = 1: 313 vs 317 ms per 1 M pairs).
+    // COATI_GPU_ROWS_DIRECT=0 / 1 forces the copy / the kernel.
+    int rows_direct = -1;
+    uint32_t rows_ctas = 64;  // COATI_GPU_ROWS_CTAS: grid of rows_to_host_kernel (16: 319.5 ms, 64: 316.7 ms)
     uint32_t force_r = 0;  // COATI_GPU_FORCE_R: rows per lane of every inter-pair fill (tuning)
     uint32_t wave_r = 0;  // COATI_GPU_WAVE_R: force rows-per-lane of the wavefront kernel (tuning)
     bool forward_generic = false;  // COATI_GPU_FORWARD_GENERIC=1: the any-k Forward kernel also for k = 1 (A/B)
@@ -359,6 +367,10 @@ struct coati_gpu_batch {
     std::vector<PairResult> h_init;     // records of the pairs rejected by host-side validation
     std::vector<uint32_t> rejected;     // their indices (caller order)
     bool rejected_known = false;
+    // device-visible addresses of the caller's page-locked row arenas (this batch's slice), set by the pipelined
+    // calls: rows_to_host_kernel then writes the used bytes of the rows there and no D2H copy of the rows
+    // follows
+    char *h_out_a = nullptr, *h_out_b = nullptr;
     std::vector<cudaEvent_t> events;  // 4 per run: fill start, fill end, traceback end, compact end
     ~coati_gpu_batch() {
         for(cudaEvent_t e : events) cudaEventDestroy(e);
@@ -439,6 +451,8 @@ extern "C" int coati_gpu_init(int device, coati_gpu_ctx** out) {
     }
     if(const char* env = std::getenv("COATI_GPU_NO_WAVE")) ctx->no_wave = env[0] == '1';
     if(const char* env = std::getenv("COATI_GPU_TB_SERIAL")) ctx->tb_serial = env[0] == '1';
+    if(const char* env = std::getenv("COATI_GPU_ROWS_DIRECT")) ctx->rows_direct = env[0] == '0' ? 0 : 1;
+    if(const char* env = std::getenv("COATI_GPU_ROWS_CTAS")) ctx->rows_ctas = (uint32_t)std::max(1, std::atoi(env));
     if(const char* env = std::getenv("COATI_GPU_FORCE_R")) ctx->force_r = (uint32_t)std::atoi(env);
     if(const char* env = std::getenv("COATI_GPU_WAVE_R")) {
         const uint32_t r = (uint32_t)std::atoi(env);
@@ -487,6 +501,10 @@ extern "C" const char* coati_gpu_last_cuda_error(coati_gpu_ctx* ctx) {
 }
 extern "C" void* coati_gpu_stream(coati_gpu_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 extern "C" uint64_t coati_gpu_launch_count(coati_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void coati_gpu_transfer_bytes(coati_gpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+    if(h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
+    if(d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
+}
 
 extern "C" int coati_gpu_device_info(coati_gpu_ctx* ctx, int* sm_count, int* clock_khz,
                                      size_t* free_bytes, size_t* total_bytes) {
@@ -833,6 +851,7 @@ static int batch_create_on(coati_gpu_ctx* ctx, cudaStream_t stream, cudaStream_t
     if(npairs) {
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_pairs.p, bt->descs.data(), npairs * sizeof(PairDesc),
                                     cudaMemcpyHostToDevice, bt->stream));  // descs outlive the copy (member)
+        ctx->h2d_bytes += npairs * sizeof(PairDesc) + bt->long_list.size() * sizeof(uint32_t);
     }
     if(!bt->long_list.empty())
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_long_list.p, bt->long_list.data(), bt->long_list.size() * sizeof(uint32_t),
@@ -856,6 +875,7 @@ extern "C" int coati_gpu_batch_upload(coati_gpu_batch* bt, const uint8_t* a_all,
         if(bt->b_total)
             CU_TRY(ctx, cudaMemcpyAsync(bt->d_des.p, des_all, bt->b_total, cudaMemcpyHostToDevice, s));
         bt->nc = 16;
+        ctx->h2d_bytes += bt->a_total + bt->b_total;
         return COATI_GPU_OK;
     }
     if((bt->a_total && (!a_all || !anc_all)) || (bt->b_total && (!b_all || !des_all)))
@@ -880,6 +900,7 @@ extern "C" int coati_gpu_batch_upload(coati_gpu_batch* bt, const uint8_t* a_all,
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_b.p, b_all, bt->b_total, cudaMemcpyHostToDevice, s));
         CU_TRY(ctx, cudaMemcpyAsync(bt->d_des.p, des_all, bt->b_total, cudaMemcpyHostToDevice, s));
     }
+    ctx->h2d_bytes += 2 * (bt->a_total + bt->b_total);
     return COATI_GPU_OK;
 }
 
@@ -1061,6 +1082,13 @@ extern "C" int coati_gpu_batch_run(coati_gpu_batch* bt) {
                                                          bt->d_des.p, bt->d_out_a.p, bt->d_out_b.p,
                                                          bt->d_results.p, ctx->gap.stop_gap,
                                                          ctx->tb_serial ? 0u : 1u);
+        if(bt->h_out_a) {  // the used bytes of every row of the chunk, straight into the caller's arenas
+            const uint32_t want = (ccnt + R2H_THREADS / 32 - 1) / (R2H_THREADS / 32);
+            rows_to_host_kernel<<<std::min(want, ctx->rows_ctas), R2H_THREADS, 0, s>>>(
+                bt->d_pairs.p, ch.first, ch.last, bt->d_out_a.p, bt->d_out_b.p, bt->h_out_a, bt->h_out_b,
+                bt->d_results.p);
+            ++bt->launches;
+        }
         cudaEventRecord(cev[3], s);
         ++bt->launches;
     }
@@ -1073,10 +1101,15 @@ static int batch_download_async(coati_gpu_batch* bt, char* out_a, char* out_b) {
     coati_gpu_ctx* ctx = bt->ctx;
     cudaStream_t s = bt->stream;
     if(bt->npairs == 0) return COATI_GPU_OK;
-    if(out_a)
+    if(out_a && !bt->h_out_a) {  // (rows written by rows_to_host_kernel are already there)
         CU_TRY(ctx, cudaMemcpyAsync(out_a, bt->d_out_a.p, bt->out_total, cudaMemcpyDeviceToHost, s));
-    if(out_b)
+        ctx->d2h_bytes += bt->out_total;
+    }
+    if(out_b && !bt->h_out_b) {
         CU_TRY(ctx, cudaMemcpyAsync(out_b, bt->d_out_b.p, bt->out_total, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += bt->out_total;
+    }
+    ctx->d2h_bytes += bt->npairs * sizeof(PairResult);
     CU_TRY(ctx, cudaMemcpyAsync(bt->h_results, bt->d_results.p, bt->npairs * sizeof(PairResult),
                                 cudaMemcpyDeviceToHost, s));
     return COATI_GPU_OK;
@@ -1214,6 +1247,7 @@ struct BatchArgs {
     int32_t* status;
     bool raw_mode;
     const uint32_t* model;
+    bool shared_link = false;  // the call is one share of a batch that other devices work on at the same time
 };
 
 #ifndef COATI_GPU_TAIL_SPLIT
@@ -1286,6 +1320,24 @@ static void plan_chunks(size_t npairs, const uint64_t* a_off, const uint64_t* b_
     for(size_t j : order) out.push_back(r[j]), cost.push_back(c[j]);
 }
 
+// The address the current device may use for host memory [p, p + bytes), or nullptr when the range is not
+// page-locked and mapped as a whole (pageable memory, or two registrations side by side).
+static char* device_view(char* p, uint64_t bytes) {
+    if(!p || !bytes) return nullptr;
+    cudaPointerAttributes first{}, last{};
+    void* dev = nullptr;
+    if(cudaPointerGetAttributes(&first, p) != cudaSuccess ||
+       cudaPointerGetAttributes(&last, p + bytes - 1) != cudaSuccess ||
+       first.type != cudaMemoryTypeHost || last.type != cudaMemoryTypeHost || !first.devicePointer ||
+       !last.devicePointer ||
+       static_cast<char*>(last.devicePointer) - static_cast<char*>(first.devicePointer) != (ptrdiff_t)(bytes - 1) ||
+       cudaHostGetDevicePointer(&dev, p, 0) != cudaSuccess || dev != first.devicePointer) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return static_cast<char*>(dev);
+}
+
 static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQueue& q, bool pipelined);
 
 static int viterbi_batch_impl(coati_gpu_ctx* ctx, size_t npairs, const uint8_t* a_all,
@@ -1354,6 +1406,15 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
         for(void*& z : zone) z = ctx->hpool.take((q.max_pairs + 1) * sizeof(PairResult));
         for(void* z : zone) ctx->hpool.give(z);
     }
+    // Row arenas the device can address (page-locked and mapped, first to last byte): a kernel writes the rows
+    // there, used bytes only, instead of a D2H copy of the padded slots (rows_to_host_kernel)
+    char *dev_out_a = nullptr, *dev_out_b = nullptr;
+    if((ctx->rows_direct > 0 || (ctx->rows_direct < 0 && A.shared_link)) && npairs && A.out_a && A.out_b) {
+        const uint64_t total = a_off[npairs] + b_off[npairs] + npairs;
+        dev_out_a = device_view(A.out_a, total);
+        dev_out_b = dev_out_a ? device_view(A.out_b, total) : nullptr;
+        if(!dev_out_b) dev_out_a = nullptr;
+    }
     const bool trace = trace_on();
     auto mark = [&](const char* what, size_t j) { trace_mark(what, j); };
     auto finish = [&](int slot) -> int {
@@ -1366,12 +1427,15 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
             ctx->last_error = cudaGetErrorString(cudaGetLastError());
             rc = COATI_GPU_E_CUDA;
         }
+        uint64_t row_bytes = 0;
         for(size_t p = 0; rc == COATI_GPU_OK && p < b->npairs; ++p) {
             const PairResult& r = b->h_results[p];
             if(A.out_len) A.out_len[first[slot] + p] = r.len;
             if(A.score) A.score[first[slot] + p] = r.score;
             if(A.status) A.status[first[slot] + p] = r.status;
+            row_bytes += (r.status == 0 ? r.len : 0) + 1;
         }
+        if(b->h_out_a) ctx->d2h_bytes += 2 * row_bytes;  // what rows_to_host_kernel wrote over the link
         if(trace && rc == COATI_GPU_OK) {
             double fill = 0, tb = 0, ex = 0;
             coati_gpu_batch_timing(b, &fill, &tb, &ex, nullptr);
@@ -1425,6 +1489,13 @@ static int viterbi_batch_pipeline(coati_gpu_ctx* ctx, const BatchArgs& A, RangeQ
         if(rc != COATI_GPU_OK) break;
         mark("plan end", p0);
         const uint64_t ao = npairs ? a_off[p0] : 0, bo = npairs ? b_off[p0] : 0;
+        if(dev_out_a) {
+            // not for a sub-batch with wavefront pairs: one warp per pair would send a 100 kB row 512 bytes at a
+            // time, and the rows of such pairs are small beside their lattices anyway -- the copy serves them
+            bool wave = false;
+            for(const Run& r : bt[slot]->runs) wave = wave || (r.cfg & CFG_WAVE);
+            if(!wave) bt[slot]->h_out_a = dev_out_a + ao + bo + p0, bt[slot]->h_out_b = dev_out_b + ao + bo + p0;
+        }
         rc = coati_gpu_batch_upload(bt[slot], A.a_all ? A.a_all + ao : nullptr, A.b_all ? A.b_all + bo : nullptr,
                                     A.anc_all ? A.anc_all + ao : nullptr, A.des_all ? A.des_all + bo : nullptr);
         mark("upload enqueued", p0);
@@ -1500,7 +1571,7 @@ extern "C" int coati_gpu_multi_alignpair_batch(coati_gpu_ctx* const* ctxs, int n
         return coati_gpu_alignpair_batch(ctxs[0], npairs, anc_all, anc_off, des_all, des_off, out_a, out_b, out_len,
                                          score, status);
     const BatchArgs A{npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b, out_len, score,
-                      status, true, nullptr};
+                      status, true, nullptr, true};
     RangeQueue q;
     try {
         std::vector<std::pair<size_t, size_t>> chunks;
@@ -1551,14 +1622,16 @@ extern "C" int coati_gpu_alignpair_batch_ranges(coati_gpu_ctx* ctx, size_t npair
                                                 const uint64_t* first, const uint64_t* last) {
     if(!ctx || !ctx->model_set || (npairs && (!anc_off || !des_off || !anc_all || !des_all))) return COATI_GPU_E_ARG;
     if(n_ranges && (!first || !last)) return COATI_GPU_E_ARG;
-    const BatchArgs A{npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b, out_len, score,
-                      status, true, nullptr};
+    BatchArgs A{npairs, nullptr, anc_off, nullptr, des_off, anc_all, des_all, out_a, out_b, out_len, score,
+                status, true, nullptr};
     RangeQueue q;
+    size_t covered = 0;
     for(size_t j = 0; j < n_ranges; ++j) {
         if(first[j] > last[j] || last[j] > npairs) return COATI_GPU_E_ARG;
-        if(first[j] < last[j]) q.add(first[j], last[j], anc_off, des_off);
+        if(first[j] < last[j]) q.add(first[j], last[j], anc_off, des_off), covered += last[j] - first[j];
     }
     if(q.ranges.empty()) return COATI_GPU_OK;
+    A.shared_link = covered < npairs;  // a shard: the rest of the batch is some other device's, at the same time
     return viterbi_batch_pipeline(ctx, A, q, true);
 }
 
@@ -1568,7 +1641,7 @@ extern "C" int coati_gpu_alignpair_batch_ranges(coati_gpu_ctx* ctx, size_t npair
 // std::string / std::vector either allocates its arenas here or registers them once.
 extern "C" void* coati_gpu_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    if(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
@@ -1579,7 +1652,7 @@ extern "C" void coati_gpu_host_free(void* p) {
 }
 extern "C" int coati_gpu_host_register(void* p, size_t bytes) {
     if(!p || !bytes) return COATI_GPU_E_ARG;
-    if(cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    if(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
         cudaGetLastError();
         return COATI_GPU_E_CUDA;
     }

@@ -423,6 +423,58 @@ expand_rows_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t 
     }
 }
 
+// Rows -> the caller's page-locked arenas (device-visible host memory), written by the GPU itself instead of a
+// D2H copy of the output buffers.  A pair's rows own La + Lb + 1 bytes per row and use about half of it, and a
+// contiguous copy cannot skip the padding: sending only the bytes that exist halves what a step puts on PCIe
+// (1.69 -> 0.87 GB per 1 M pairs of C5), which is what bounds the end-to-end figure from four GPUs up (DESIGN.md
+// section 5).  Runs after the expansion kernels (rows and final lengths are in device memory), as a SMALL
+// persistent grid: a CTA that waits on the link must not take the place of a fill CTA on every SM (the
+// one-stage form of this -- every expansion warp writing to the host, 16 k CTAs -- cost the concurrent fills
+// 11 ms per 1 M pairs).  One warp per pair; the link wants large writes, so a lane gathers sixteen bytes of
+// the row (byte loads, L1 hits: device and host slots need not be aligned alike) and stores them as one aligned
+// 16-byte word, 512 bytes per warp and instruction; a 16-byte unit shared with the neighbouring slot (the first and
+// the last of a row) leaves as ONE instruction of sixteen lanes, a byte each -- contiguous bytes of one sector.
+constexpr uint32_t R2H_THREADS = 256;
+__global__ void __launch_bounds__(R2H_THREADS)
+rows_to_host_kernel(const PairDesc* __restrict__ pairs, uint32_t first, uint32_t last,
+                    const char* __restrict__ d_out_a, const char* __restrict__ d_out_b,
+                    char* __restrict__ h_out_a, char* __restrict__ h_out_b,
+                    const PairResult* __restrict__ results) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for(uint32_t p = first + warp; p < last; p += nwarp) {
+        const PairDesc pd = pairs[p];
+        const PairResult res = results[pd.orig];
+        const uint32_t n_out = (res.status == 0 ? res.len : 0u) + 1u;  // columns (end stops included), NUL
+#pragma unroll
+        for(int i = 0; i < 2; ++i) {
+            const char* src = (i ? d_out_b : d_out_a) + pd.out_off;
+            char* dst = (i ? h_out_b : h_out_a) + pd.out_off;
+            // the row lives at v = x + mis of the 16-byte aligned address al; its bytes are v in [mis, hi)
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u), hi = mis + n_out;
+            char* al = dst - mis;
+            for(uint32_t base = 0; base < hi; base += 512u) {  // (warp-uniform trip count)
+                const uint32_t v0 = base + 16u * lane;
+                const bool full = v0 >= mis && v0 + 16u <= hi;
+                if(full) {
+                    const unsigned char* s8 = reinterpret_cast<const unsigned char*>(src) + (v0 - mis);
+                    uint32_t w[4];
+#pragma unroll
+                    for(int q = 0; q < 4; ++q)
+                        w[q] = (uint32_t)s8[4 * q] | ((uint32_t)s8[4 * q + 1] << 8) |
+                               ((uint32_t)s8[4 * q + 2] << 16) | ((uint32_t)s8[4 * q + 3] << 24);
+                    *reinterpret_cast<uint4*>(al + v0) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                uint32_t part = __ballot_sync(0xffffffffu, !full && v0 < hi && v0 + 16u > mis);
+                for(; part; part &= part - 1u) {
+                    const uint32_t v = base + 16u * (uint32_t)(__ffs(part) - 1) + lane;
+                    if(lane < 16u && v >= mis && v < hi) al[v] = src[v - mis];
+                }
+            }
+        }
+    }
+}
+
 // Long pairs: one warp per segment between two checkpoints of traceback_burst_kernel (ops in `ops`, rows
 // written left-aligned into the pair's output slots); the warp of the last segment also restores the end
 // stops and terminates the rows, as expand_rows_kernel does.

@@ -51,6 +51,10 @@ const char* coati_gpu_last_cuda_error(coati_gpu_ctx* ctx);
 void* coati_gpu_stream(coati_gpu_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t coati_gpu_launch_count(coati_gpu_ctx* ctx);
+/* bytes the batch calls of this context moved host->device and device->host since creation (bench.py's
+ * h2d_bytes_per_step / d2h_bytes_per_step): copies as enqueued, and -- where the rows are written straight into
+ * page-locked caller arenas, see coati_gpu_host_alloc -- the row bytes actually written (length + terminator) */
+void coati_gpu_transfer_bytes(coati_gpu_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 int coati_gpu_device_info(coati_gpu_ctx* ctx, int* sm_count, int* clock_khz, size_t* free_bytes,
                           size_t* total_bytes);
 
@@ -128,7 +132,11 @@ int coati_gpu_alignpair_batch_ranges(coati_gpu_ctx* ctx, size_t npairs, const ch
                                      size_t n_ranges, const uint64_t* first, const uint64_t* last);
 
 /* Page-locked host memory for the arenas of the batch calls (they overlap copies and kernels only from and
- * to pinned memory): allocate here, or register memory the caller already owns. */
+ * to pinned memory): allocate here, or register memory the caller already owns.  The memory is also mapped for the
+ * device: a call that is one share of a multi-device batch (coati_gpu_multi_alignpair_batch with several
+ * contexts, coati_gpu_alignpair_batch_ranges on part of a batch) has the GPU write the rows into such arenas
+ * itself, used bytes only; bytes of a slot beyond a row's terminator are then left as the caller had them
+ * (with the copy they are scratch).  COATI_GPU_ROWS_DIRECT=1 / 0 forces that / the copy for every call. */
 void* coati_gpu_host_alloc(size_t bytes);
 void coati_gpu_host_free(void* p);
 int coati_gpu_host_register(void* p, size_t bytes);
