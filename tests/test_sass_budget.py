@@ -73,3 +73,25 @@ def test_interior_step_budget(header, kernel, f2, steps, max_per_step, max_regs)
     # the decisions are sign bits pushed by funnel shifts: five per cell (rows per lane = FADD2 per step / 6.5)
     cells = round(f2 / 6.5) if "pipe3" not in kernel else 6
     assert loop["ops"]["SHF"] >= 5 * cells * steps
+
+
+def test_rows_to_host_kernel_writes_16_byte_words():
+    """rows_to_host_kernel (traceback.cuh) is bound by the host link, which wants large writes: the bulk of a row
+    must leave as 16-byte stores (STG.128), the kernel must stay small enough to sit beside the fills (<= 32
+    registers, no shared memory, no spill)."""
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, "k.cu"), "w") as f:
+        f.write('#include "%s/coati_b200/csrc/traceback.cuh"\n' % ROOT)
+    r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-cubin",
+                        "-Xptxas", "-v", "-o", os.path.join(d, "k.cubin"), os.path.join(d, "k.cu")],
+                       capture_output=True, text=True, check=True)
+    info = r.stderr[r.stderr.index("rows_to_host_kernel"):]
+    info = info[:info.index("Compile time")]
+    assert int(re.search(r"Used (\d+) registers", info).group(1)) <= 32
+    assert "0 bytes spill stores" in info and "smem" not in info
+    sass = subprocess.check_output(["cuobjdump", "-sass", os.path.join(d, "k.cubin")]).decode()
+    shutil.rmtree(d, ignore_errors=True)
+    sass = sass[sass.index("rows_to_host_kernel"):]
+    sass = sass[:sass.index("Function :", 20)] if "Function :" in sass[20:] else sass
+    assert re.search(r"STG\.E\.128", sass), "rows leave as 16-byte words"
+    assert len(re.findall(r"LDG\.E\.U8", sass)) >= 16, "sixteen independent byte loads per word"
