@@ -161,6 +161,13 @@ def cpu_reference_run(wl, npairs_total, seconds, procs, table, first=0, lib=None
                        f"{cells:.3g} cells), viterbi_mem+traceback_viterbi, {procs} processes x 1 thread, {flags}")
 
 
+def workload_config(wl, npairs):
+    """`config` of the JSON line: what was measured, identical in both arms (the driver compares them); what is
+    particular to a run -- shards, arenas, chunk counts -- goes into `run`."""
+    return {"workload": wl["desc"], "pairs": npairs, "k": wl["k"], "seed": wl["seed"],
+            "l2": "GPU arm: inputs + decision stream of a step >> 126 MB L2 (no flush needed)"}
+
+
 def run_reference(args, wl, table):
     rank, world, local = dist_env()
     if rank != 0:
@@ -182,7 +189,7 @@ def run_reference(args, wl, table):
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "pairs_per_s": sum(v["pairs"] for v in timed) / secs,
-        "config": {"workload": wl["desc"], "pairs": npairs, "k": wl["k"], "seed": wl["seed"]},
+        "config": workload_config(wl, npairs),
         "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": last["cores"], "kind": last["kind"],
                          "sample": last["sample"]},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -500,25 +507,27 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "pairs_per_s": npairs * args.steps / secs,
-        "config": {"workload": wl["desc"], "pairs": npairs, "k": wl["k"], "seed": wl["seed"],
-                   "cells": cells_total, "l2": "inputs + decision stream >> 126 MB L2 (no flush needed)",
-                   "sharding": ("one batch; contiguous chunks, heaviest first, greedy LPT on sum(La*Lb) over ranks "
-                                "(coati_gpu_plan_shards)" if strong else "rank r owns pairs [r*P, (r+1)*P)"),
-                   "chunks": int(len(r_first)),
-                   "shard_cells_max_over_mean": max(shard_cells) / (sum(shard_cells) / world),
-                   "decision_stream_bytes_rank0": stats["dir_bytes"], "dir_chunks_rank0": stats["chunks"],
-                   "gen_seconds": gen_s,
-                   "host_arena": "/dev/shm + cudaHostRegister" if arena_shared else "cudaHostAlloc",
-                   "host_arena_pinned": bool(arena_pinned),
-                   "collective": None if dist is None else ("NCCL send/recv gather of rows + result records to rank 0, "
-                                                            "double-buffered staging copy, side stream"),
-                   "nccl_gather_bytes_to_root_per_step": gather_bytes},
+        "config": workload_config(wl, npairs),
+        "run": {"cells": cells_total,
+                "sharding": ("one batch; contiguous chunks, heaviest first, greedy LPT on sum(La*Lb) over ranks "
+                             "(coati_gpu_plan_shards)" if strong else "rank r owns pairs [r*P, (r+1)*P)"),
+                "chunks": int(len(r_first)),
+                "shard_cells_max_over_mean": max(shard_cells) / (sum(shard_cells) / world),
+                "decision_stream_bytes_rank0": stats["dir_bytes"], "dir_chunks_rank0": stats["chunks"],
+                "gen_seconds": gen_s,
+                "host_arena": "/dev/shm + cudaHostRegister" if arena_shared else "cudaHostAlloc",
+                "host_arena_pinned": bool(arena_pinned),
+                "collective": None if dist is None else ("NCCL send/recv gather of rows + result records to rank 0, "
+                                                         "double-buffered staging copy, side stream"),
+                "nccl_gather_bytes_to_root_per_step": gather_bytes},
         "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "pairs_per_s": npairs * e2e_steps / e2e_s,
                 "steps": e2e_steps, "ms_per_step_by_rank": [round(x, 2) for x in e2e_rank_ms],
                 "api": "coati_gpu_alignpair_batch_ranges, rows delivered to one host arena",
-                "row_delivery": ("expansion kernel writes the used bytes of every row into the page-locked arena"
-                                 if arena_pinned and os.environ.get("COATI_GPU_ROWS_DIRECT", "1") != "0"
+                # the library's default: the kernel for a share of a multi-device batch, the copy otherwise
+                "row_delivery": ("rows_to_host_kernel writes the used bytes of every row into the page-locked arena"
+                                 if arena_pinned and (os.environ.get("COATI_GPU_ROWS_DIRECT") == "1" or
+                                                      (os.environ.get("COATI_GPU_ROWS_DIRECT") is None and world > 1))
                                  else "D2H copy of the padded slots")},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
